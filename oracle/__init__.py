@@ -1,0 +1,1 @@
+"""ORACLE package: test infrastructure only.  See oracle/README.md."""
