@@ -1,0 +1,491 @@
+// C-ABI of the engine (include/spriteworld_b200.h): engine/raster lifetime, scene upload,
+// kernel launches.  No torch types; plain CUDA runtime.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "swb_device.cuh"
+#include "swb_render.cuh"
+#include "swb_step.cuh"
+#include "swb_tables.h"
+
+using namespace swb;
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_error = buf;
+  return 1;
+}
+
+#define CUDA_TRY(expr)                                                              \
+  do {                                                                              \
+    cudaError_t _e = (expr);                                                        \
+    if (_e != cudaSuccess)                                                          \
+      return fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+template <typename T>
+cudaError_t dev_alloc(T **p, size_t n) {
+  cudaError_t e = cudaMalloc(reinterpret_cast<void **>(p), (n ? n : 1) * sizeof(T));
+  if (e == cudaSuccess) e = cudaMemset(*p, 0, (n ? n : 1) * sizeof(T));
+  return e;
+}
+
+const void *g_cfg_owner = nullptr;  // which engine's StepCfg sits in constant memory
+
+}  // namespace
+
+struct swb_engine {
+  swb_config cfg;
+  StepCfg step_cfg;
+  DevState st;
+  int device = 0;
+  int max_spans = 1;  // 1 while every uploaded shape is convex, else 4
+  int64_t launches = 0;
+  // staging for scene uploads (device), grown on demand
+  size_t stage_cap = 0;
+  double *g_f64 = nullptr;    // [8][cap*S]
+  uint32_t *g_member = nullptr;
+  uint8_t *g_u8 = nullptr;    // [2][cap*S]
+  uint32_t *g_rgb = nullptr;
+  float *g_factors = nullptr;
+  int32_t *g_dst = nullptr;   // [cap] destination scene index e*K+k
+  std::vector<void *> owned;
+  // buffers of swb_step_host
+  void *h_actions = nullptr;
+  swb_step_out h_out = {nullptr, nullptr, nullptr, nullptr};
+  uint8_t *h_frames = nullptr;
+  size_t h_frames_bytes = 0;
+};
+
+struct swb_raster {
+  swb_engine *eng;
+  RasterDev rd;
+  AxisHost ax, ay;
+  int smem_rows = 0;
+  std::vector<void *> owned;
+};
+
+namespace {
+
+__global__ void scatter_scenes_kernel(DevState st, int n, const int32_t *__restrict__ dst,
+                                      const double *__restrict__ f64, size_t f64_stride,
+                                      const uint32_t *__restrict__ member,
+                                      const uint8_t *__restrict__ u8, size_t u8_stride,
+                                      const uint32_t *__restrict__ rgb,
+                                      const float *__restrict__ factors) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * st.S) return;
+  const int sc = i / st.S, s = i - sc * st.S;
+  const size_t d = (size_t)dst[sc] * st.S + s;
+  st.p_x[d] = f64[0 * f64_stride + i];
+  st.p_y[d] = f64[1 * f64_stride + i];
+  st.p_m00[d] = f64[2 * f64_stride + i];
+  st.p_m01[d] = f64[3 * f64_stride + i];
+  st.p_m10[d] = f64[4 * f64_stride + i];
+  st.p_m11[d] = f64[5 * f64_stride + i];
+  st.p_vx[d] = f64[6 * f64_stride + i];
+  st.p_vy[d] = f64[7 * f64_stride + i];
+  st.p_member[d] = member[i];
+  st.p_shape[d] = u8[0 * u8_stride + i];
+  st.p_pos_f32[d] = u8[1 * u8_stride + i];
+  st.p_rgb[d] = rgb[i];
+  for (int f = 0; f < 5; ++f) st.p_factors[d * 5 + f] = factors[(size_t)i * 5 + f];
+}
+
+int ensure_step_cfg(swb_engine *eng) {
+  if (g_cfg_owner != eng) {
+    CUDA_TRY(cudaMemcpyToSymbol(c_step, &eng->step_cfg, sizeof(StepCfg)));
+    g_cfg_owner = eng;
+  }
+  return 0;
+}
+
+template <typename T>
+int upload_vec(swb_raster *r, const std::vector<T> &v, const T **out) {
+  T *p = nullptr;
+  CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&p), std::max<size_t>(v.size(), 1) * sizeof(T)));
+  r->owned.push_back(p);
+  CUDA_TRY(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *out = p;
+  return 0;
+}
+
+int upload_axis(swb_raster *r, const AxisHost &h, AxisTables *d) {
+  if (upload_vec(r, h.win_min, &d->win_min)) return 1;
+  if (upload_vec(r, h.win_len, &d->win_len)) return 1;
+  if (upload_vec(r, h.win_cls, &d->win_cls)) return 1;
+  if (upload_vec(r, h.prefix, &d->prefix)) return 1;
+  if (upload_vec(r, h.program, &d->program)) return 1;
+  if (upload_vec(r, h.first_out, &d->first_out)) return 1;
+  if (upload_vec(r, h.last_out, &d->last_out)) return 1;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *swb_last_error(void) { return g_error.c_str(); }
+int swb_version(void) { return 1; }
+int swb_sizeof_config(void) { return (int)sizeof(swb_config); }
+int swb_sizeof_task_node(void) { return (int)sizeof(swb_task_node); }
+
+int swb_engine_create(const swb_config *cfg, swb_engine **out) {
+  if (!cfg || !out) return fail("swb_engine_create: null argument");
+  if (cfg->n_envs < 1) return fail("n_envs must be >= 1");
+  if (cfg->n_slots < 1 || cfg->n_slots > SWB_MAX_SLOTS)
+    return fail("n_slots must be in [1, %d], got %d", SWB_MAX_SLOTS, cfg->n_slots);
+  if (cfg->pool_depth < 1) return fail("pool_depth must be >= 1");
+  if (cfg->n_nodes < 1 || cfg->n_nodes > SWB_MAX_NODES) return fail("bad n_nodes %d", cfg->n_nodes);
+  for (int i = 0; i < cfg->n_nodes; ++i) {
+    const swb_task_node &nd = cfg->nodes[i];
+    if (nd.kind == SWB_TASK_META) {
+      if (nd.n_children < 0 || nd.n_children > SWB_MAX_CHILDREN) return fail("bad n_children");
+      for (int c = 0; c < nd.n_children; ++c)
+        if (nd.children[c] < 0 || nd.children[c] >= i) return fail("task tree is not post-order");
+    } else if (nd.kind == SWB_TASK_CLUSTERING) {
+      if (nd.n_clusters < 1 || nd.n_clusters > SWB_MAX_CHILDREN) return fail("bad n_clusters");
+    } else if (nd.kind == SWB_TASK_FIND_GOAL) {
+      if (nd.filter_slot >= SWB_MAX_FILTERS) return fail("bad filter_slot");
+    } else if (nd.kind != SWB_TASK_NO_REWARD) {
+      return fail("unknown task kind %d", nd.kind);
+    }
+  }
+  if (cfg->action_kind < 0 || cfg->action_kind > SWB_ACT_EMBODIED) return fail("bad action_kind");
+  int n_dev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&n_dev));
+  if (cfg->device < 0 || cfg->device >= n_dev) return fail("no CUDA device %d", cfg->device);
+  CUDA_TRY(cudaSetDevice(cfg->device));
+
+  swb_engine *eng = new swb_engine();
+  eng->cfg = *cfg;
+  eng->device = cfg->device;
+  StepCfg &sc = eng->step_cfg;
+  memset(&sc, 0, sizeof sc);
+  sc.action_kind = cfg->action_kind;
+  sc.action_scale = cfg->action_scale;
+  sc.motion_cost = cfg->motion_cost;
+  sc.keep_in_frame = cfg->keep_in_frame;
+  sc.max_episode_length = cfg->max_episode_length;
+  sc.n_nodes = cfg->n_nodes;
+  memcpy(sc.nodes, cfg->nodes, sizeof(swb_task_node) * cfg->n_nodes);
+
+  DevState &st = eng->st;
+  memset(&st, 0, sizeof st);
+  st.E = cfg->n_envs;
+  st.S = cfg->n_slots;
+  st.K = cfg->pool_depth;
+  const size_t ES = (size_t)st.E * st.S, EKS = ES * st.K;
+  bool ok = true;
+  auto A = [&](auto **p, size_t n) {
+    if (ok && dev_alloc(p, n) != cudaSuccess) ok = false;
+    if (ok) eng->owned.push_back(*p);
+  };
+  A(&st.pos_x, ES); A(&st.pos_y, ES);
+  A(&st.cursor, st.E); A(&st.step_count, st.E);
+  A(&st.reset_next, st.E + 4); A(&st.render_status, st.E + 4);
+  A(&st.p_x, EKS); A(&st.p_y, EKS);
+  A(&st.p_m00, EKS); A(&st.p_m01, EKS); A(&st.p_m10, EKS); A(&st.p_m11, EKS);
+  A(&st.p_vx, EKS); A(&st.p_vy, EKS);
+  A(&st.p_member, EKS); A(&st.p_shape, EKS); A(&st.p_pos_f32, EKS); A(&st.p_rgb, EKS);
+  A(&st.p_factors, EKS * 5);
+  double *d_verts = nullptr;
+  int32_t *d_nv = nullptr;
+  A(&d_verts, (size_t)SWB_NUM_SHAPES * SWB_MAX_VERTS * 2);
+  A(&d_nv, SWB_NUM_SHAPES);
+  if (!ok) {
+    swb_engine_destroy(eng);
+    return fail("device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  for (int s = 1; s < SWB_NUM_SHAPES; ++s)
+    if (cfg->shape_n_verts[s] < 0 || cfg->shape_n_verts[s] > SWB_MAX_VERTS) {
+      swb_engine_destroy(eng);
+      return fail("shape %d has %d vertices (max %d)", s, cfg->shape_n_verts[s], SWB_MAX_VERTS);
+    }
+  CUDA_TRY(cudaMemcpy(d_verts, cfg->shape_verts, sizeof cfg->shape_verts, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(d_nv, cfg->shape_n_verts, sizeof cfg->shape_n_verts, cudaMemcpyHostToDevice));
+  st.shape_verts = d_verts;
+  st.shape_n = d_nv;
+  // every env starts "about to reset" (environment.py:70)
+  CUDA_TRY(cudaMemset(st.reset_next, 1, st.E));
+  *out = eng;
+  return 0;
+}
+
+void swb_engine_destroy(swb_engine *eng) {
+  if (!eng) return;
+  cudaSetDevice(eng->device);
+  for (void *p : eng->owned) cudaFree(p);
+  cudaFree(eng->g_f64); cudaFree(eng->g_member); cudaFree(eng->g_u8); cudaFree(eng->g_rgb);
+  cudaFree(eng->g_factors); cudaFree(eng->g_dst);
+  cudaFree(eng->h_actions); cudaFree(eng->h_out.reward); cudaFree(eng->h_out.step_type);
+  cudaFree(eng->h_out.success); cudaFree(eng->h_out.status); cudaFree(eng->h_frames);
+  if (g_cfg_owner == eng) g_cfg_owner = nullptr;
+  delete eng;
+}
+
+int swb_upload_scenes(swb_engine *eng, const swb_scene_soa *sc, const int32_t *env_ids,
+                      const int32_t *ring_slots, int32_t n, void *stream_) {
+  if (!eng || !sc || !env_ids || !ring_slots) return fail("swb_upload_scenes: null argument");
+  if (n <= 0) return 0;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CUDA_TRY(cudaSetDevice(eng->device));
+  const int S = eng->st.S;
+  const size_t nS = (size_t)n * S;
+  std::vector<int32_t> dst(n);
+  for (int i = 0; i < n; ++i) {
+    if (env_ids[i] < 0 || env_ids[i] >= eng->st.E) return fail("env id %d out of range", env_ids[i]);
+    if (ring_slots[i] < 0 || ring_slots[i] >= eng->st.K) return fail("ring slot %d out of range", ring_slots[i]);
+    dst[i] = env_ids[i] * eng->st.K + ring_slots[i];
+  }
+  for (size_t i = 0; i < nS; ++i) {
+    const int sh = sc->shape[i];
+    if (sh >= SWB_NUM_SHAPES) return fail("shape id %d out of range", sh);
+    if (sh > 6) eng->max_spans = 4;  // stars / spokes: several spans per canvas row
+    if (sh && eng->cfg.shape_n_verts[sh] < 3) return fail("shape %d has no vertex table", sh);
+  }
+  if ((size_t)n > eng->stage_cap) {
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    cudaFree(eng->g_f64); cudaFree(eng->g_member); cudaFree(eng->g_u8); cudaFree(eng->g_rgb);
+    cudaFree(eng->g_factors); cudaFree(eng->g_dst);
+    eng->stage_cap = 0;
+    const size_t cap = (size_t)n, capS = cap * S;
+    CUDA_TRY(cudaMalloc(&eng->g_f64, capS * 8 * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&eng->g_member, capS * sizeof(uint32_t)));
+    CUDA_TRY(cudaMalloc(&eng->g_u8, capS * 2));
+    CUDA_TRY(cudaMalloc(&eng->g_rgb, capS * sizeof(uint32_t)));
+    CUDA_TRY(cudaMalloc(&eng->g_factors, capS * 5 * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&eng->g_dst, cap * sizeof(int32_t)));
+    eng->stage_cap = cap;
+  }
+  const size_t stride = eng->stage_cap * S;
+  const double *f64_src[8] = {sc->x, sc->y, sc->m00, sc->m01, sc->m10, sc->m11, sc->vx, sc->vy};
+  for (int a = 0; a < 8; ++a) {
+    if (!f64_src[a]) return fail("swb_upload_scenes: null f64 array %d", a);
+    CUDA_TRY(cudaMemcpyAsync(eng->g_f64 + a * stride, f64_src[a], nS * sizeof(double),
+                             cudaMemcpyHostToDevice, stream));
+  }
+  if (!sc->member || !sc->shape || !sc->pos_f32 || !sc->rgb) return fail("swb_upload_scenes: null array");
+  CUDA_TRY(cudaMemcpyAsync(eng->g_member, sc->member, nS * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+  CUDA_TRY(cudaMemcpyAsync(eng->g_u8, sc->shape, nS, cudaMemcpyHostToDevice, stream));
+  CUDA_TRY(cudaMemcpyAsync(eng->g_u8 + stride, sc->pos_f32, nS, cudaMemcpyHostToDevice, stream));
+  std::vector<uint32_t> rgb(nS);
+  for (size_t i = 0; i < nS; ++i)
+    rgb[i] = (uint32_t)sc->rgb[3 * i] | ((uint32_t)sc->rgb[3 * i + 1] << 8) | ((uint32_t)sc->rgb[3 * i + 2] << 16);
+  CUDA_TRY(cudaMemcpyAsync(eng->g_rgb, rgb.data(), nS * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+  if (sc->factors) {
+    CUDA_TRY(cudaMemcpyAsync(eng->g_factors, sc->factors, nS * 5 * sizeof(float), cudaMemcpyHostToDevice, stream));
+  } else {
+    CUDA_TRY(cudaMemsetAsync(eng->g_factors, 0, nS * 5 * sizeof(float), stream));
+  }
+  CUDA_TRY(cudaMemcpyAsync(eng->g_dst, dst.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+  const int threads = 256, blocks = (int)((nS + threads - 1) / threads);
+  scatter_scenes_kernel<<<blocks, threads, 0, stream>>>(eng->st, n, eng->g_dst, eng->g_f64, stride,
+                                                        eng->g_member, eng->g_u8, stride, eng->g_rgb,
+                                                        eng->g_factors);
+  eng->launches++;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaStreamSynchronize(stream));  // host staging vectors die here
+  return 0;
+}
+
+int swb_request_reset(swb_engine *eng, const uint8_t *mask, void *stream_) {
+  if (!eng) return fail("null engine");
+  CUDA_TRY(cudaSetDevice(eng->device));
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  request_reset_kernel<<<(eng->st.E + 255) / 256, 256, 0, stream>>>(eng->st, mask);
+  eng->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int swb_step(swb_engine *eng, const void *actions, int32_t action_dtype, const swb_step_out *out,
+             void *stream_) {
+  if (!eng || !actions || !out) return fail("swb_step: null argument");
+  if (!out->reward || !out->step_type || !out->success || !out->status)
+    return fail("swb_step: every swb_step_out pointer must be set");
+  const bool emb = eng->cfg.action_kind == SWB_ACT_EMBODIED;
+  if (emb && action_dtype != SWB_DTYPE_I32) return fail("Embodied actions must be int32 [E][2]");
+  if (!emb && action_dtype != SWB_DTYPE_F32 && action_dtype != SWB_DTYPE_F64)
+    return fail("SelectMove/DragAndDrop actions must be float32 or float64 [E][4]");
+  CUDA_TRY(cudaSetDevice(eng->device));
+  if (ensure_step_cfg(eng)) return 1;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int blocks = (eng->st.E + STEP_WARPS - 1) / STEP_WARPS;
+  step_kernel<<<blocks, STEP_WARPS * 32, 0, stream>>>(eng->st, actions, action_dtype, *out);
+  eng->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int swb_raster_create(swb_engine *eng, int32_t width, int32_t height, int32_t aa,
+                      const uint8_t bg_rgb[3], swb_raster **out) {
+  if (!eng || !out) return fail("swb_raster_create: null argument");
+  if (width < 1 || height < 1 || width > 4096 || height > 4096) return fail("bad image size %dx%d", width, height);
+  if (aa < 1) return fail("anti_aliasing must be >= 1");
+  if ((int64_t)width * aa > 4095 || (int64_t)height * aa > 4095)
+    return fail("canvas %dx%d exceeds 4095 pixels per side", width * aa, height * aa);
+  CUDA_TRY(cudaSetDevice(eng->device));
+  swb_raster *r = new swb_raster();
+  r->eng = eng;
+  std::string err;
+  if (!build_axis(width * aa, width, &r->ax, &err) || !build_axis(height * aa, height, &r->ay, &err)) {
+    delete r;
+    return fail("%s", err.c_str());
+  }
+  RasterDev &rd = r->rd;
+  rd.W = width; rd.H = height; rd.aa = aa; rd.CW = width * aa; rd.CH = height * aa;
+  rd.bg = bg_rgb ? ((uint32_t)bg_rgb[0] | ((uint32_t)bg_rgb[1] << 8) | ((uint32_t)bg_rgb[2] << 16)) : 0u;
+  rd.band_rows = height <= 64 ? height : 64;
+  rd.n_bands = (height + rd.band_rows - 1) / rd.band_rows;
+  rd.max_spans = 1;
+  int rows = 0;
+  for (int b = 0; b < rd.n_bands; ++b) {
+    const int y0 = b * rd.band_rows, y1 = std::min(y0 + rd.band_rows, height) - 1;
+    rows = std::max(rows, r->ay.win_min[y1] + r->ay.win_len[y1] - r->ay.win_min[y0]);
+  }
+  r->smem_rows = rows;
+  if (upload_axis(r, r->ax, &rd.ax) || upload_axis(r, r->ay, &rd.ay)) {
+    swb_raster_destroy(r);
+    return 1;
+  }
+  *out = r;
+  return 0;
+}
+
+void swb_raster_destroy(swb_raster *r) {
+  if (!r) return;
+  for (void *p : r->owned) cudaFree(p);
+  delete r;
+}
+
+static int launch_render(swb_engine *eng, swb_raster *r, uint8_t *frames, uint8_t *status,
+                         cudaStream_t stream) {
+  if (r->eng != eng) return fail("raster belongs to another engine");
+  RasterDev rd = r->rd;
+  rd.max_spans = eng->max_spans;
+  const RenderLayout L(eng->st.S, r->smem_rows, rd.max_spans, rd.band_rows, rd.W, rd.aa);
+  int max_smem = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, eng->device));
+  if (L.total > max_smem)
+    return fail("render needs %d B of shared memory per CTA (limit %d): too many sprite slots / too large a canvas",
+                L.total, max_smem);
+  CUDA_TRY(cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+  DevState st = eng->st;
+  st.render_status = status;
+  dim3 grid(eng->st.E, rd.n_bands);
+  render_kernel<<<grid, R_THREADS, L.total, stream>>>(st, rd, frames, r->smem_rows);
+  eng->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int swb_render(swb_engine *eng, swb_raster *r, uint8_t *frames, void *stream_) {
+  if (!eng || !r || !frames) return fail("swb_render: null argument");
+  CUDA_TRY(cudaSetDevice(eng->device));
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CUDA_TRY(cudaMemsetAsync(eng->st.render_status, 0, eng->st.E, stream));
+  return launch_render(eng, r, frames, eng->st.render_status, stream);
+}
+
+int swb_step_render(swb_engine *eng, swb_raster *r, const void *actions, int32_t action_dtype,
+                    const swb_step_out *out, uint8_t *frames, void *stream_) {
+  if (!r || !frames) return fail("swb_step_render: null argument");
+  if (swb_step(eng, actions, action_dtype, out, stream_)) return 1;
+  return launch_render(eng, r, frames, out->status, static_cast<cudaStream_t>(stream_));
+}
+
+int swb_step_host(swb_engine *eng, swb_raster *r, const void *actions, int32_t action_dtype,
+                  double *reward, int8_t *step_type, uint8_t *success, uint8_t *status,
+                  uint8_t *frames, void *stream_) {
+  if (!eng || !actions) return fail("swb_step_host: null argument");
+  CUDA_TRY(cudaSetDevice(eng->device));
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int E = eng->st.E;
+  if (!eng->h_actions) {
+    CUDA_TRY(cudaMalloc(&eng->h_actions, (size_t)E * 4 * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&eng->h_out.reward, (size_t)E * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&eng->h_out.step_type, E + 4));
+    CUDA_TRY(cudaMalloc(&eng->h_out.success, E + 4));
+    CUDA_TRY(cudaMalloc(&eng->h_out.status, E + 4));
+  }
+  const size_t abytes = action_dtype == SWB_DTYPE_I32 ? (size_t)E * 2 * 4
+                        : (action_dtype == SWB_DTYPE_F32 ? (size_t)E * 16 : (size_t)E * 32);
+  CUDA_TRY(cudaMemcpyAsync(eng->h_actions, actions, abytes, cudaMemcpyHostToDevice, stream));
+  if (r) {
+    const size_t fbytes = (size_t)E * r->rd.H * r->rd.W * 3;
+    if (fbytes > eng->h_frames_bytes) {
+      CUDA_TRY(cudaStreamSynchronize(stream));
+      cudaFree(eng->h_frames);
+      eng->h_frames_bytes = 0;
+      CUDA_TRY(cudaMalloc(&eng->h_frames, fbytes));
+      eng->h_frames_bytes = fbytes;
+    }
+    if (swb_step_render(eng, r, eng->h_actions, action_dtype, &eng->h_out, eng->h_frames, stream)) return 1;
+    if (frames) CUDA_TRY(cudaMemcpyAsync(frames, eng->h_frames, fbytes, cudaMemcpyDeviceToHost, stream));
+  } else {
+    if (swb_step(eng, eng->h_actions, action_dtype, &eng->h_out, stream)) return 1;
+  }
+  if (reward) CUDA_TRY(cudaMemcpyAsync(reward, eng->h_out.reward, (size_t)E * sizeof(double), cudaMemcpyDeviceToHost, stream));
+  if (step_type) CUDA_TRY(cudaMemcpyAsync(step_type, eng->h_out.step_type, E, cudaMemcpyDeviceToHost, stream));
+  if (success) CUDA_TRY(cudaMemcpyAsync(success, eng->h_out.success, E, cudaMemcpyDeviceToHost, stream));
+  if (status) CUDA_TRY(cudaMemcpyAsync(status, eng->h_out.status, E, cudaMemcpyDeviceToHost, stream));
+  CUDA_TRY(cudaStreamSynchronize(stream));
+  return 0;
+}
+
+int swb_state_pointers(swb_engine *eng, double **pos_x, double **pos_y, int32_t **cursor,
+                       int32_t **step_count, uint8_t **reset_next) {
+  if (!eng) return fail("null engine");
+  if (pos_x) *pos_x = eng->st.pos_x;
+  if (pos_y) *pos_y = eng->st.pos_y;
+  if (cursor) *cursor = eng->st.cursor;
+  if (step_count) *step_count = eng->st.step_count;
+  if (reset_next) *reset_next = eng->st.reset_next;
+  return 0;
+}
+
+int swb_download_state(swb_engine *eng, double *pos_x, double *pos_y, int32_t *cursor,
+                       int32_t *step_count, uint8_t *reset_next, void *stream_) {
+  if (!eng) return fail("null engine");
+  CUDA_TRY(cudaSetDevice(eng->device));
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const size_t ES = (size_t)eng->st.E * eng->st.S;
+  if (pos_x) CUDA_TRY(cudaMemcpyAsync(pos_x, eng->st.pos_x, ES * 8, cudaMemcpyDeviceToHost, stream));
+  if (pos_y) CUDA_TRY(cudaMemcpyAsync(pos_y, eng->st.pos_y, ES * 8, cudaMemcpyDeviceToHost, stream));
+  if (cursor) CUDA_TRY(cudaMemcpyAsync(cursor, eng->st.cursor, eng->st.E * 4, cudaMemcpyDeviceToHost, stream));
+  if (step_count) CUDA_TRY(cudaMemcpyAsync(step_count, eng->st.step_count, eng->st.E * 4, cudaMemcpyDeviceToHost, stream));
+  if (reset_next) CUDA_TRY(cudaMemcpyAsync(reset_next, eng->st.reset_next, eng->st.E, cudaMemcpyDeviceToHost, stream));
+  CUDA_TRY(cudaStreamSynchronize(stream));
+  return 0;
+}
+
+int swb_upload_state(swb_engine *eng, const double *pos_x, const double *pos_y, const int32_t *cursor,
+                     const int32_t *step_count, const uint8_t *reset_next, void *stream_) {
+  if (!eng) return fail("null engine");
+  CUDA_TRY(cudaSetDevice(eng->device));
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const size_t ES = (size_t)eng->st.E * eng->st.S;
+  if (pos_x) CUDA_TRY(cudaMemcpyAsync(eng->st.pos_x, pos_x, ES * 8, cudaMemcpyHostToDevice, stream));
+  if (pos_y) CUDA_TRY(cudaMemcpyAsync(eng->st.pos_y, pos_y, ES * 8, cudaMemcpyHostToDevice, stream));
+  if (cursor) CUDA_TRY(cudaMemcpyAsync(eng->st.cursor, cursor, eng->st.E * 4, cudaMemcpyHostToDevice, stream));
+  if (step_count) CUDA_TRY(cudaMemcpyAsync(eng->st.step_count, step_count, eng->st.E * 4, cudaMemcpyHostToDevice, stream));
+  if (reset_next) CUDA_TRY(cudaMemcpyAsync(eng->st.reset_next, reset_next, eng->st.E, cudaMemcpyHostToDevice, stream));
+  CUDA_TRY(cudaStreamSynchronize(stream));
+  return 0;
+}
+
+int64_t swb_launch_count(const swb_engine *eng) { return eng ? eng->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,472 @@
+// Render kernel: PILRenderer.render for E envs (renderers/pil_renderer.py:67-91).
+//
+// One CTA renders one band of one frame.  Nothing of the aa-times supersampled canvas is
+// ever materialised; the CTA works on what Pillow's two stages are functions of:
+//
+//   A  vertices   int(canvas * (R.S.v + pos)) in fp64 (sprite.py:128-133, pil_renderer.py:81,
+//                 Pillow's (int) truncation), then Pillow's edge records (float32 dx).
+//   B  spans      per (sprite, canvas row): Pillow's scan conversion (sorted float32 edge
+//                 crossings, ROUND_UP/ROUND_DOWN span ends, duplicated end points, the
+//                 corner-joining refinement, horizontal edges) -> <= M [xs, xe] spans.
+//   C  per sprite region (the outputs whose 2-D tap window can see the sprite), in tiles
+//      of 16x16 outputs:
+//        H  horizontal LANCZOS pass of the canvas rows the tile needs.  A canvas row is
+//           piecewise constant, so an output is  bg*K + sum_runs (colour-bg) * (P[b]-P[a])
+//           with P the prefix sums of the 22-bit tap vector; occlusion is resolved front
+//           to back with a <=32-bit coverage mask of the tap window.  Result clip8'ed to
+//           uint8 exactly like Pillow's intermediate image.
+//        V  vertical pass over the tile's H values (paired taps: equal coefficients share
+//           one multiply), clip8, written into the frame staged in shared memory.
+//   D  the staged frame (background + tiles) goes to HBM as 128-bit stores, rows flipped
+//      (np.flipud, pil_renderer.py:90).
+//
+// All pixel arithmetic is integer and associative, so the result is bit-identical to
+// Pillow's; the float32 edge arithmetic uses explicit _rn intrinsics (no FMA).
+#pragma once
+#include <climits>
+
+#include "swb_device.cuh"
+
+namespace swb {
+
+constexpr int R_THREADS = 256;
+constexpr int TILE_Y = 16;
+constexpr int TILE_X = 16;
+constexpr int MAX_CROSS = 40;   // edge crossings kept per (sprite, row)
+constexpr int MAX_ROW_SPANS = 12;
+
+struct RenderLayout {
+  int S, rows, M, band_rows, W, aa;
+  int off_pos, off_meta, off_iv, off_edge_i, off_edge_f, off_edge_flag, off_region;
+  int off_rowmask, off_spans, off_htile, off_frame, total;
+  int ht_rows;
+  __host__ __device__ RenderLayout(int S_, int rows_, int M_, int band_rows_, int W_, int aa_)
+      : S(S_), rows(rows_), M(M_), band_rows(band_rows_), W(W_), aa(aa_) {
+    int o = 0;
+    auto take = [&](int bytes) { int r = o; o += (bytes + 15) & ~15; return r; };
+    off_pos = take(S * 6 * 8);
+    off_meta = take(S * 12 * 4);
+    off_iv = take(S * SWB_MAX_VERTS * 2 * 4);
+    off_edge_i = take(S * SWB_MAX_VERTS * 4 * 4);
+    off_edge_f = take(S * SWB_MAX_VERTS * 4);
+    off_edge_flag = take(S * SWB_MAX_VERTS);
+    off_region = take(S * 4 * 2);
+    off_rowmask = take(rows * 4);
+    off_spans = take(S * rows * M * 4);
+    ht_rows = TILE_Y * aa + 32;
+    off_htile = take(ht_rows * TILE_X * 8);
+    off_frame = take(band_rows * W * 3);
+    total = o;
+  }
+};
+
+__device__ __forceinline__ int round_up_f(float f) {
+  return f >= 0.0f ? (int)floorf(__fadd_rn(f, 0.5f)) : -(int)floorf(__fadd_rn(fabsf(f), 0.5f));
+}
+__device__ __forceinline__ int round_down_f(float f) {
+  return f >= 0.0f ? (int)ceilf(__fsub_rn(f, 0.5f)) : -(int)ceilf(__fsub_rn(fabsf(f), 0.5f));
+}
+__device__ __forceinline__ float edge_x_at(int y, int y0, float dx, int x0) {
+  return __fadd_rn(__fmul_rn((float)(y - y0), dx), (float)x0);
+}
+__device__ __forceinline__ uint32_t clip8_q22(int v) {
+  v >>= 22;
+  return (uint32_t)min(max(v, 0), 255);
+}
+
+// merges [xs, xe] into a small unsorted list of disjoint, non-adjacent spans
+__device__ __forceinline__ void add_span(int *lxs, int *lxe, int &n, int xs, int xe, bool &ovf) {
+  for (int i = 0; i < n;) {
+    if (xs <= lxe[i] + 1 && lxs[i] <= xe + 1) {
+      xs = min(xs, lxs[i]);
+      xe = max(xe, lxe[i]);
+      lxs[i] = lxs[n - 1];
+      lxe[i] = lxe[n - 1];
+      --n;
+      i = 0;
+    } else {
+      ++i;
+    }
+  }
+  if (n < MAX_ROW_SPANS) {
+    lxs[n] = xs;
+    lxe[n] = xe;
+    ++n;
+  } else {
+    ovf = true;
+  }
+}
+
+// Pillow polygon_generic for one canvas row of one sprite.  Returns the number of spans.
+__device__ int scan_row(const int *ex0, const int *ey0, const int *eymin, const int *eymax,
+                        const float *edx, const uint8_t *eflag, int ne, int y, int p_ymax,
+                        int CW, int *lxs, int *lxe, bool &ovf) {
+  float xx[MAX_CROSS];
+  int j = 0;
+  int n = 0;
+  for (int i = 0; i < ne; ++i) {
+    const int fl = eflag[i];
+    if (fl == 1) {  // horizontal edge: drawn directly as hline(xmin, y, xmax)
+      if (ey0[i] == y) {
+        int xs = max(eymin[i], 0), xe = min(eymax[i], CW - 1);  // (xmin,xmax stored here)
+        if (xs <= xe) add_span(lxs, lxe, n, xs, xe, ovf);
+      }
+      continue;
+    }
+    if (fl != 2) continue;
+    if (y < eymin[i] || y > eymax[i]) continue;
+    const float dx = edx[i];
+    const float x = edge_x_at(y, ey0[i], dx, ex0[i]);
+    if (j < MAX_CROSS) xx[j] = x; else ovf = true;
+    ++j;
+    if (y == eymax[i] && y < p_ymax) {
+      if (j < MAX_CROSS) xx[j] = x; else ovf = true;
+      ++j;
+    } else if (dx != 0.0f) {
+      const bool cur_start = (y == eymin[i]);
+      const bool cur_end_last = (y == p_ymax && y == eymax[i]);
+      if (cur_start || cur_end_last) {
+        int xi = 0;
+        for (int k = 0; k < i; ++k) {
+          if (eflag[k] != 2) continue;
+          const int my = xi;
+          if (y >= eymin[k] && y <= eymax[k]) xi += (y == eymax[k] && y < p_ymax) ? 2 : 1;
+          const float odx = edx[k];
+          if ((dx > 0.0f && odx <= 0.0f) || (dx < 0.0f && odx >= 0.0f)) continue;
+          const bool both_start = cur_start && (y == eymin[k]);
+          const bool both_end = cur_end_last && (y == eymax[k]);
+          if (!both_start && !both_end) continue;
+          const float ox = edge_x_at(y, ey0[k], odx, ex0[k]);
+          if (roundf(x) != roundf(ox)) continue;
+          const int off = (y == p_ymax) ? -1 : 1;
+          const float adj = edge_x_at(y + off, ey0[i], dx, ex0[i]);
+          const float adjo = edge_x_at(y + off, ey0[k], odx, ex0[k]);
+          const bool right = (y == eymax[i]) ? (dx < 0.0f) : (dx > 0.0f);
+          float nv = right ? __fsub_rn(fminf(adj, adjo), 1.0f) : __fadd_rn(fmaxf(adj, adjo), 1.0f);
+          nv = floorf(__fadd_rn(nv, 0.5f));
+          nv = right ? fmaxf(nv, x) : fminf(nv, x);
+          if (my < MAX_CROSS) xx[my] = nv;
+          break;
+        }
+      }
+    }
+  }
+  if (j > MAX_CROSS) j = MAX_CROSS;
+  for (int a = 1; a < j; ++a) {  // insertion sort, ascending
+    float v = xx[a];
+    int b = a - 1;
+    while (b >= 0 && xx[b] > v) { xx[b + 1] = xx[b]; --b; }
+    xx[b + 1] = v;
+  }
+  int x_pos = 0;
+  for (int i = 1; i < j; i += 2) {
+    const int x_end = round_down_f(xx[i]);
+    if (x_end < x_pos) continue;
+    if (xx[i - 1] > (float)x_pos) {
+      x_pos = round_up_f(xx[i - 1]);
+      if (x_end < x_pos) continue;
+    }
+    int xs = max(x_pos, 0), xe = min(x_end, CW - 1);
+    if (xs <= xe) add_span(lxs, lxe, n, xs, xe, ovf);
+    x_pos = x_end + 1;
+  }
+  return n;
+}
+
+__global__ void __launch_bounds__(R_THREADS)
+render_kernel(DevState st, RasterDev rd, uint8_t *__restrict__ frames, int smem_rows) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int e = blockIdx.x;
+  const int band = blockIdx.y;
+  const int tid = threadIdx.x;
+  const int S = st.S;
+  const RenderLayout L(S, smem_rows, rd.max_spans, rd.band_rows, rd.W, rd.aa);
+  const int M = rd.max_spans;
+
+  double *s_px = reinterpret_cast<double *>(smem + L.off_pos);
+  double *s_py = s_px + S;
+  double *s_m = s_py + S;  // [4][S]
+  int *s_nv = reinterpret_cast<int *>(smem + L.off_meta);
+  int *s_rgb = s_nv + S;
+  int *s_xmin = s_rgb + S, *s_xmax = s_xmin + S, *s_gymin = s_xmax + S, *s_gymax = s_gymin + S;
+  int *s_pymin = s_gymax + S, *s_pymax = s_pymin + S, *s_ne = s_pymax + S, *s_shape = s_ne + S;
+  int *s_r0 = s_shape + S, *s_rcnt = s_r0 + S;
+  int *s_ivx = reinterpret_cast<int *>(smem + L.off_iv);
+  int *s_ivy = s_ivx + S * SWB_MAX_VERTS;
+  int *e_x0 = reinterpret_cast<int *>(smem + L.off_edge_i);
+  int *e_y0 = e_x0 + S * SWB_MAX_VERTS;
+  int *e_ymin = e_y0 + S * SWB_MAX_VERTS;
+  int *e_ymax = e_ymin + S * SWB_MAX_VERTS;
+  float *e_dx = reinterpret_cast<float *>(smem + L.off_edge_f);
+  uint8_t *e_flag = smem + L.off_edge_flag;
+  short *s_region = reinterpret_cast<short *>(smem + L.off_region);  // [S][4] yo0,yo1,xo0,xo1
+  uint32_t *s_rowmask = reinterpret_cast<uint32_t *>(smem + L.off_rowmask);
+  uint32_t *s_spans = reinterpret_cast<uint32_t *>(smem + L.off_spans);
+  uint2 *s_ht = reinterpret_cast<uint2 *>(smem + L.off_htile);
+  uint8_t *s_frame = smem + L.off_frame;
+  __shared__ int s_overflow;
+
+  const int yo_b0 = band * rd.band_rows;
+  const int yo_b1 = min(yo_b0 + rd.band_rows, rd.H);
+  const int n_yo = yo_b1 - yo_b0;
+  // canvas rows this band's vertical windows can touch
+  const int row_b0 = rd.ay.win_min[yo_b0];
+  const int row_b1 = rd.ay.win_min[yo_b1 - 1] + rd.ay.win_len[yo_b1 - 1];  // exclusive
+  const int n_rows = row_b1 - row_b0;
+
+  // ---- phase 0: sprite records of this env's current scene ---------------------
+  if (tid == 0) s_overflow = 0;
+  if (tid < S) {
+    const int scene = (e * st.K + st.cursor[e]) * S + tid;
+    const int shape = st.p_shape[scene];
+    s_shape[tid] = shape;
+    s_nv[tid] = shape ? st.shape_n[shape] : 0;
+    s_rgb[tid] = (int)st.p_rgb[scene];
+    s_px[tid] = st.pos_x[e * S + tid];
+    s_py[tid] = st.pos_y[e * S + tid];
+    s_m[0 * S + tid] = st.p_m00[scene];
+    s_m[1 * S + tid] = st.p_m01[scene];
+    s_m[2 * S + tid] = st.p_m10[scene];
+    s_m[3 * S + tid] = st.p_m11[scene];
+  }
+  for (int i = tid; i < n_rows; i += R_THREADS) s_rowmask[i] = 0u;
+  for (int i = tid; i < S * n_rows * M; i += R_THREADS) s_spans[i] = 0x0000FFFFu;  // xs > xe
+  {  // background fill of the staged frame
+    const uint32_t r = rd.bg & 255u, g = (rd.bg >> 8) & 255u, b = (rd.bg >> 16) & 255u;
+    const int n_bytes = n_yo * rd.W * 3;
+    if ((rd.bg & 0xFFFFFFu) == 0u || (r == g && g == b)) {
+      const uint32_t w = r * 0x01010101u;
+      uint32_t *f32 = reinterpret_cast<uint32_t *>(s_frame);
+      for (int i = tid; i < (n_bytes + 3) / 4; i += R_THREADS) f32[i] = w;
+    } else {
+      for (int i = tid; i < n_yo * rd.W; i += R_THREADS) {
+        s_frame[3 * i] = (uint8_t)r; s_frame[3 * i + 1] = (uint8_t)g; s_frame[3 * i + 2] = (uint8_t)b;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- phase A1: integer canvas vertices ----------------------------------------
+  for (int t = tid; t < S * SWB_MAX_VERTS; t += R_THREADS) {
+    const int s = t / SWB_MAX_VERTS, i = t % SWB_MAX_VERTS;
+    if (i < s_nv[s]) {
+      const double *v = st.shape_verts + ((size_t)s_shape[s] * SWB_MAX_VERTS + i) * 2;
+      const double vx = v[0], vy = v[1];
+      // centred path (sprite.py:96-101): (a*x + c*y) + 0 ; world (sprite.py:128-133): + pos
+      const double cx = __dadd_rn(__dadd_rn(__dmul_rn(s_m[0 * S + s], vx), __dmul_rn(s_m[1 * S + s], vy)), 0.0);
+      const double cy = __dadd_rn(__dadd_rn(__dmul_rn(s_m[2 * S + s], vx), __dmul_rn(s_m[3 * S + s], vy)), 0.0);
+      const double wx = __dadd_rn(cx, s_px[s]), wy = __dadd_rn(cy, s_py[s]);
+      // canvas_size * vertices (pil_renderer.py:81), then Pillow's (int) cast
+      s_ivx[t] = __double2int_rz(__dmul_rn((double)rd.CW, wx));
+      s_ivy[t] = __double2int_rz(__dmul_rn((double)rd.CH, wy));
+    }
+  }
+  __syncthreads();
+
+  // ---- phase A2: edge records (Pillow add_edge) + per-sprite extents -------------
+  for (int t = tid; t < S * SWB_MAX_VERTS; t += R_THREADS) {
+    const int s = t / SWB_MAX_VERTS, i = t % SWB_MAX_VERTS;
+    const int nv = s_nv[s];
+    int flag = 0;
+    if (i < nv) {
+      const int j = (i + 1 == nv) ? 0 : i + 1;
+      const int x0 = s_ivx[s * SWB_MAX_VERTS + i], y0 = s_ivy[s * SWB_MAX_VERTS + i];
+      const int x1 = s_ivx[s * SWB_MAX_VERTS + j], y1 = s_ivy[s * SWB_MAX_VERTS + j];
+      // the closing edge exists only if the last vertex differs from the first
+      const bool exists = (i + 1 < nv) || (x0 != x1 || y0 != y1);
+      if (exists) {
+        e_x0[t] = x0;
+        e_y0[t] = y0;
+        if (y0 == y1) {
+          flag = 1;
+          e_ymin[t] = min(x0, x1);  // horizontal edges keep (xmin, xmax) here
+          e_ymax[t] = max(x0, x1);
+          e_dx[t] = 0.0f;
+        } else {
+          flag = 2;
+          e_ymin[t] = min(y0, y1);
+          e_ymax[t] = max(y0, y1);
+          e_dx[t] = __fdiv_rn((float)(x1 - x0), (float)(y1 - y0));
+        }
+      }
+    }
+    e_flag[t] = (uint8_t)flag;
+  }
+  if (tid < S) {
+    const int nv = s_nv[tid];
+    int xmn = INT_MAX, xmx = INT_MIN, ymn = INT_MAX, ymx = INT_MIN;
+    for (int i = 0; i < nv; ++i) {
+      const int x = s_ivx[tid * SWB_MAX_VERTS + i], y = s_ivy[tid * SWB_MAX_VERTS + i];
+      xmn = min(xmn, x); xmx = max(xmx, x); ymn = min(ymn, y); ymx = max(ymx, y);
+    }
+    s_xmin[tid] = xmn; s_xmax[tid] = xmx; s_gymin[tid] = ymn; s_gymax[tid] = ymx;
+    // Pillow: ymin = min(ysize-1, edges), ymax = max(0, edges); then clip to [0, ysize]
+    int pymin = min(rd.CH - 1, ymn), pymax = max(0, ymx);
+    pymin = max(pymin, 0);
+    pymax = min(pymax, rd.CH);
+    s_pymin[tid] = pymin; s_pymax[tid] = pymax;
+    s_ne[tid] = nv;
+    {
+      const int r0 = max(pymin, row_b0), r1 = min(min(pymax, rd.CH - 1), row_b1 - 1);
+      s_r0[tid] = r0;
+      s_rcnt[tid] = (nv > 0 && r1 >= r0) ? (r1 - r0 + 1) : 0;
+    }
+    // output region whose 2-D tap window can see this sprite's bounding box
+    short yo0 = 0, yo1 = -1, xo0 = 0, xo1 = -1;
+    if (nv > 0 && xmx >= 0 && xmn < rd.CW && ymx >= 0 && ymn < rd.CH) {
+      const int cx0 = max(xmn, 0), cx1 = min(xmx, rd.CW - 1);
+      const int cy0 = max(ymn, 0), cy1 = min(ymx, rd.CH - 1);
+      xo0 = rd.ax.first_out[cx0]; xo1 = rd.ax.last_out[cx1];
+      yo0 = max((int)rd.ay.first_out[cy0], yo_b0);
+      yo1 = min((int)rd.ay.last_out[cy1], yo_b1 - 1);
+    }
+    s_region[tid * 4 + 0] = yo0; s_region[tid * 4 + 1] = yo1;
+    s_region[tid * 4 + 2] = xo0; s_region[tid * 4 + 3] = xo1;
+  }
+  __syncthreads();
+
+  // ---- phase B: spans per (sprite, canvas row) -----------------------------------
+  {
+    int total = 0;
+    for (int s = 0; s < S; ++s) total += s_rcnt[s];
+    for (int t = tid; t < total; t += R_THREADS) {
+      int s = 0, rem = t;
+      while (rem >= s_rcnt[s]) { rem -= s_rcnt[s]; ++s; }
+      const int y = s_r0[s] + rem;
+      int lxs[MAX_ROW_SPANS], lxe[MAX_ROW_SPANS];
+      bool ovf = false;
+      const int base = s * SWB_MAX_VERTS;
+      const int n = scan_row(e_x0 + base, e_y0 + base, e_ymin + base, e_ymax + base, e_dx + base,
+                             e_flag + base, s_ne[s], y, s_pymax[s], rd.CW, lxs, lxe, ovf);
+      if (n > M) ovf = true;
+      uint32_t *dst = s_spans + ((size_t)s * n_rows + (y - row_b0)) * M;
+      for (int k = 0; k < min(n, M); ++k) dst[k] = (uint32_t)lxs[k] | ((uint32_t)lxe[k] << 16);
+      if (n > 0) atomicOr(&s_rowmask[y - row_b0], 1u << s);
+      if (ovf) s_overflow = 1;
+    }
+  }
+  __syncthreads();
+
+  // ---- phase C: per sprite region, tiles of TILE_Y x TILE_X outputs ----------------
+  const uint32_t bg_r = rd.bg & 255u, bg_g = (rd.bg >> 8) & 255u, bg_b = (rd.bg >> 16) & 255u;
+  for (int s = 0; s < S; ++s) {
+    const int ryo0 = s_region[s * 4 + 0], ryo1 = s_region[s * 4 + 1];
+    const int rxo0 = s_region[s * 4 + 2], rxo1 = s_region[s * 4 + 3];
+    if (ryo1 < ryo0 || rxo1 < rxo0) continue;
+    for (int ty0 = ryo0; ty0 <= ryo1; ty0 += TILE_Y) {
+      const int ny = min(TILE_Y, ryo1 - ty0 + 1);
+      const int tr0 = rd.ay.win_min[ty0];
+      const int tr1 = rd.ay.win_min[ty0 + ny - 1] + rd.ay.win_len[ty0 + ny - 1];  // exclusive
+      const int nr = tr1 - tr0;
+      for (int tx0 = rxo0; tx0 <= rxo1; tx0 += TILE_X) {
+        const int nx = min(TILE_X, rxo1 - tx0 + 1);
+        // ---- H pass ----
+        for (int it = tid; it < nr * nx; it += R_THREADS) {
+          const int r = it / nx, c = it - r * nx;
+          const int y = tr0 + r, xo = tx0 + c;
+          const uint32_t rmask = s_rowmask[y - row_b0];
+          uint32_t orr = bg_r, og = bg_g, ob = bg_b;
+          if (rmask) {
+            const int xmin = rd.ax.win_min[xo];
+            const int len = rd.ax.win_len[xo];
+            const int32_t *P = rd.ax.prefix + (int)rd.ax.win_cls[xo] * 33;
+            const uint32_t full = (len >= 32) ? 0xFFFFFFFFu : ((1u << len) - 1u);
+            const int ktot = P[len];
+            int ar = (int)bg_r * ktot, ag = (int)bg_g * ktot, ab = (int)bg_b * ktot;
+            uint32_t covered = 0u;
+            uint32_t rem = rmask;
+            while (rem && covered != full) {
+              const int sp = 31 - __clz(rem);  // front-most remaining sprite
+              rem &= ~(1u << sp);
+              const uint32_t *spn = s_spans + ((size_t)sp * n_rows + (y - row_b0)) * M;
+              uint32_t m = 0u;
+              for (int k = 0; k < M; ++k) {
+                const uint32_t w = spn[k];
+                const int xs = (int)(w & 0xFFFFu), xe = (int)(w >> 16);
+                const int a = max(xs, xmin) - xmin, b = min(xe, xmin + len - 1) - xmin;
+                if (a <= b) m |= ((2u << b) - 1u) & ~((1u << a) - 1u);
+              }
+              uint32_t vis = m & ~covered;
+              covered |= m;
+              if (vis) {
+                const uint32_t col = (uint32_t)s_rgb[sp];
+                const int dr = (int)(col & 255u) - (int)bg_r, dg = (int)((col >> 8) & 255u) - (int)bg_g,
+                          db = (int)((col >> 16) & 255u) - (int)bg_b;
+                int wsum = 0;
+                while (vis) {
+                  const int lo = __ffs(vis) - 1;
+                  const uint32_t t = vis >> lo;
+                  const int run = (t == 0xFFFFFFFFu) ? 32 : (__ffs(~t) - 1);
+                  wsum += P[lo + run] - P[lo];
+                  vis = (lo + run >= 32) ? 0u : (vis & ~((1u << (lo + run)) - 1u));
+                }
+                ar += dr * wsum; ag += dg * wsum; ab += db * wsum;
+              }
+            }
+            orr = clip8_q22(ar + (1 << 21));
+            og = clip8_q22(ag + (1 << 21));
+            ob = clip8_q22(ab + (1 << 21));
+          }
+          s_ht[r * TILE_X + c] = make_uint2(orr | (og << 16), ob);
+        }
+        __syncthreads();
+        // ---- V pass ----
+        for (int it = tid; it < ny * nx; it += R_THREADS) {
+          const int ly = it / nx, c = it - ly * nx;
+          const int yo = ty0 + ly, xo = tx0 + c;
+          const int rbase = rd.ay.win_min[yo] - tr0;
+          const int32_t *prog = rd.ay.program + (int)rd.ay.win_cls[yo] * PROG_STRIDE;
+          const int np = prog[0], ns = prog[1];
+          int ar = 1 << 21, ag = 1 << 21, ab = 1 << 21;
+          const int32_t *pp = prog + 2;
+          for (int k = 0; k < np; ++k) {
+            const int ab_idx = pp[2 * k];
+            const int kk = pp[2 * k + 1];
+            const uint2 u = s_ht[(rbase + (ab_idx & 255)) * TILE_X + c];
+            const uint2 v = s_ht[(rbase + (ab_idx >> 8)) * TILE_X + c];
+            const uint32_t rg = u.x + v.x, bb = u.y + v.y;
+            ar += (int)(rg & 0xFFFFu) * kk;
+            ag += (int)(rg >> 16) * kk;
+            ab += (int)bb * kk;
+          }
+          const int32_t *ps = prog + 2 + 2 * 16;
+          for (int k = 0; k < ns; ++k) {
+            const int a_idx = ps[2 * k];
+            const int kk = ps[2 * k + 1];
+            const uint2 u = s_ht[(rbase + a_idx) * TILE_X + c];
+            ar += (int)(u.x & 0xFFFFu) * kk;
+            ag += (int)(u.x >> 16) * kk;
+            ab += (int)u.y * kk;
+          }
+          uint8_t *px = s_frame + ((size_t)(yo - yo_b0) * rd.W + xo) * 3;
+          px[0] = (uint8_t)clip8_q22(ar);
+          px[1] = (uint8_t)clip8_q22(ag);
+          px[2] = (uint8_t)clip8_q22(ab);
+        }
+        __syncthreads();
+      }
+    }
+  }
+
+  // ---- phase D: staged frame -> HBM, rows flipped (np.flipud) ------------------------
+  uint8_t *dst_frame = frames + (size_t)e * rd.H * rd.W * 3;
+  const int row_bytes = rd.W * 3;
+  if ((row_bytes & 15) == 0) {
+    const int vec_per_row = row_bytes >> 4;
+    for (int i = tid; i < n_yo * vec_per_row; i += R_THREADS) {
+      const int ly = i / vec_per_row, v = i - ly * vec_per_row;
+      const uint4 val = reinterpret_cast<const uint4 *>(s_frame + (size_t)ly * row_bytes)[v];
+      const int out_row = rd.H - 1 - (yo_b0 + ly);
+      reinterpret_cast<uint4 *>(dst_frame + (size_t)out_row * row_bytes)[v] = val;
+    }
+  } else {
+    for (int i = tid; i < n_yo * row_bytes; i += R_THREADS) {
+      const int ly = i / row_bytes, v = i - ly * row_bytes;
+      dst_frame[(size_t)(rd.H - 1 - (yo_b0 + ly)) * row_bytes + v] = s_frame[(size_t)ly * row_bytes + v];
+    }
+  }
+  // several bands of one env may race here, but they all OR in the same bit
+  if (tid == 0 && s_overflow) st.render_status[e] |= (uint8_t)SWB_ENV_SPAN_OVERFLOW;
+}
+
+}  // namespace swb

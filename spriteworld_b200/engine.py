@@ -1,0 +1,293 @@
+"""Thin Python owner of one swb_engine (one per GPU).
+
+PyTorch is used only for device memory and streams: action, reward, flag and frame
+buffers are torch tensors whose `data_ptr()` is handed to the C-ABI
+(include/spriteworld_b200.h).  All compute happens in the CUDA library.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from spriteworld_b200 import _native
+
+SCENE_FIELDS_F64 = ('x', 'y', 'm00', 'm01', 'm10', 'm11', 'vx', 'vy')
+
+
+def _as_ptr(a):
+  return ctypes.c_void_p(a.ctypes.data)
+
+
+class StepResult(object):
+  """Per-env outputs of one step, as device tensors (valid until the next step)."""
+  __slots__ = ('reward', 'step_type', 'success', 'status', 'frames')
+
+  def __init__(self, reward, step_type, success, status, frames=None):
+    self.reward, self.step_type, self.success = reward, step_type, success
+    self.status, self.frames = status, frames
+
+
+class Raster(object):
+  """PILRenderer(image_size=(width, height), anti_aliasing, bg_color) on the device."""
+
+  def __init__(self, engine, width, height, anti_aliasing=1, bg_color=(0, 0, 0)):
+    self.engine = engine
+    self.width, self.height, self.anti_aliasing = int(width), int(height), int(anti_aliasing)
+    bg = (ctypes.c_uint8 * 3)(*[int(c) for c in bg_color])
+    h = ctypes.c_void_p()
+    _native.check(engine._lib.swb_raster_create(engine._h, self.width, self.height,
+                                                self.anti_aliasing, bg, ctypes.byref(h)))
+    self._h = h
+
+  def new_frames(self):
+    return torch.empty((self.engine.n_envs, self.height, self.width, 3), dtype=torch.uint8,
+                       device=self.engine.device)
+
+  def close(self):
+    if self._h:
+      self.engine._lib.swb_raster_destroy(self._h)
+      self._h = None
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:  # pragma: no cover
+      pass
+
+
+class Engine(object):
+
+  def __init__(self, n_envs, n_slots, pool_depth, action, nodes, shapes, keep_in_frame=True,
+               max_episode_length=1000, device=0):
+    """Args:
+      action: dict(kind='select_move'|'drag_and_drop'|'embodied', scale=.., motion_cost=..)
+      nodes: post-order list of task-node dicts (see tasks.compile_task)
+      shapes: dict name -> (V, 2) float64 vertex arrays (constants.SHAPES)
+    """
+    if not torch.cuda.is_available():
+      raise _native.NativeError('spriteworld_b200 needs a CUDA device; there is no CPU path')
+    self._lib = _native.load()
+    self.n_envs, self.n_slots, self.pool_depth = int(n_envs), int(n_slots), int(pool_depth)
+    self.device = torch.device('cuda', device)
+    self.action_kind = {'select_move': _native.ACT_SELECT_MOVE,
+                        'drag_and_drop': _native.ACT_DRAG_AND_DROP,
+                        'embodied': _native.ACT_EMBODIED}[action['kind']]
+    cfg = _native.Config()
+    cfg.device = device
+    cfg.n_envs, cfg.n_slots, cfg.pool_depth = self.n_envs, self.n_slots, self.pool_depth
+    cfg.action_kind = self.action_kind
+    cfg.action_scale = float(action['scale'])
+    cfg.motion_cost = float(action.get('motion_cost', 0.0))
+    cfg.keep_in_frame = int(bool(keep_in_frame))
+    cfg.max_episode_length = int(min(max_episode_length, 2 ** 31 - 1))
+    fill_task_nodes(cfg, nodes)
+    fill_shapes(cfg, shapes)
+    h = ctypes.c_void_p()
+    _native.check(self._lib.swb_engine_create(ctypes.byref(cfg), ctypes.byref(h)))
+    self._h = h
+    E = self.n_envs
+    self._reward = torch.zeros(E, dtype=torch.float64, device=self.device)
+    self._step_type = torch.zeros(E, dtype=torch.int8, device=self.device)
+    self._success = torch.zeros(E, dtype=torch.uint8, device=self.device)
+    self._status = torch.zeros(E, dtype=torch.uint8, device=self.device)
+    self._out = _native.StepOut(self._reward.data_ptr(), self._step_type.data_ptr(),
+                                self._success.data_ptr(), self._status.data_ptr())
+
+  # -- lifetime -------------------------------------------------------------------
+  def close(self):
+    if getattr(self, '_h', None):
+      self._lib.swb_engine_destroy(self._h)
+      self._h = None
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:  # pragma: no cover
+      pass
+
+  def _stream(self):
+    return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+  # -- scenes -----------------------------------------------------------------------
+  def upload_scenes(self, scenes, env_ids, ring_slots):
+    """scenes: dict of numpy arrays shaped (n, S[, ...]) (see scene.SceneBatch.arrays)."""
+    n = len(env_ids)
+    S = self.n_slots
+    keep = []
+
+    def arr(name, dtype, tail=()):
+      a = np.ascontiguousarray(scenes[name], dtype=dtype)
+      assert a.shape == (n, S) + tail, (name, a.shape, (n, S) + tail)
+      keep.append(a)
+      return a.ctypes.data
+
+    soa = _native.SceneSoA()
+    for f in SCENE_FIELDS_F64:
+      setattr(soa, f, arr(f, np.float64))
+    soa.member = arr('member', np.uint32)
+    soa.shape = arr('shape', np.uint8)
+    soa.pos_f32 = arr('pos_f32', np.uint8)
+    soa.rgb = arr('rgb', np.uint8, (3,))
+    soa.factors = arr('factors', np.float32, (5,)) if 'factors' in scenes else None
+    env_ids = np.ascontiguousarray(env_ids, dtype=np.int32)
+    ring_slots = np.ascontiguousarray(ring_slots, dtype=np.int32)
+    _native.check(self._lib.swb_upload_scenes(self._h, ctypes.byref(soa), _as_ptr(env_ids),
+                                              _as_ptr(ring_slots), n, self._stream()))
+
+  def request_reset(self, mask=None):
+    ptr = None
+    if mask is not None:
+      mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+      ptr = ctypes.c_void_p(mask.data_ptr())
+    _native.check(self._lib.swb_request_reset(self._h, ptr, self._stream()))
+
+  # -- stepping ---------------------------------------------------------------------
+  def _action_dtype(self, actions):
+    if self.action_kind == _native.ACT_EMBODIED:
+      if actions.dtype != torch.int32 or tuple(actions.shape) != (self.n_envs, 2):
+        raise ValueError('Embodied actions must be an int32 tensor of shape (E, 2)')
+      return _native.DTYPE_I32
+    if tuple(actions.shape) != (self.n_envs, 4):
+      raise ValueError('actions must have shape (E, 4)')
+    if actions.dtype == torch.float32:
+      return _native.DTYPE_F32
+    if actions.dtype == torch.float64:
+      return _native.DTYPE_F64
+    raise ValueError('actions must be float32 or float64')
+
+  def step(self, actions, raster=None, frames=None):
+    """One Environment.step for every env.  `actions`: device tensor."""
+    if actions.device != self.device or not actions.is_contiguous():
+      raise ValueError('actions must be a contiguous tensor on %s' % self.device)
+    dt = self._action_dtype(actions)
+    if raster is None:
+      _native.check(self._lib.swb_step(self._h, ctypes.c_void_p(actions.data_ptr()), dt,
+                                       ctypes.byref(self._out), self._stream()))
+    else:
+      if frames is None:
+        frames = raster.new_frames()
+      _native.check(self._lib.swb_step_render(
+          self._h, raster._h, ctypes.c_void_p(actions.data_ptr()), dt, ctypes.byref(self._out),
+          ctypes.c_void_p(frames.data_ptr()), self._stream()))
+    return StepResult(self._reward, self._step_type, self._success, self._status, frames)
+
+  def render(self, raster, frames=None):
+    if frames is None:
+      frames = raster.new_frames()
+    _native.check(self._lib.swb_render(self._h, raster._h, ctypes.c_void_p(frames.data_ptr()),
+                                       self._stream()))
+    return frames
+
+  def step_host(self, actions, raster=None, want_frames=True):
+    """Whole call with HOST buffers (numpy in, numpy out): H2D, step, render, D2H, sync."""
+    a = np.ascontiguousarray(actions)
+    if self.action_kind == _native.ACT_EMBODIED:
+      a = np.ascontiguousarray(a, dtype=np.int32)
+      dt = _native.DTYPE_I32
+    elif a.dtype == np.float32:
+      dt = _native.DTYPE_F32
+    else:
+      a = np.ascontiguousarray(a, dtype=np.float64)
+      dt = _native.DTYPE_F64
+    E = self.n_envs
+    reward = np.empty(E, np.float64)
+    step_type = np.empty(E, np.int8)
+    success = np.empty(E, np.uint8)
+    status = np.empty(E, np.uint8)
+    frames = None
+    if raster is not None and want_frames:
+      frames = np.empty((E, raster.height, raster.width, 3), np.uint8)
+    _native.check(self._lib.swb_step_host(
+        self._h, raster._h if raster is not None else None, _as_ptr(a), dt, _as_ptr(reward),
+        _as_ptr(step_type), _as_ptr(success), _as_ptr(status),
+        _as_ptr(frames) if frames is not None else None, self._stream()))
+    return reward, step_type, success, status, frames
+
+  # -- state ------------------------------------------------------------------------
+  def download_state(self):
+    E, S = self.n_envs, self.n_slots
+    px, py = np.empty((E, S)), np.empty((E, S))
+    cursor, count = np.empty(E, np.int32), np.empty(E, np.int32)
+    reset_next = np.empty(E, np.uint8)
+    _native.check(self._lib.swb_download_state(self._h, _as_ptr(px), _as_ptr(py), _as_ptr(cursor),
+                                               _as_ptr(count), _as_ptr(reset_next),
+                                               self._stream()))
+    return dict(pos_x=px, pos_y=py, cursor=cursor, step_count=count, reset_next=reset_next)
+
+  def upload_state(self, pos_x=None, pos_y=None, cursor=None, step_count=None, reset_next=None):
+    def p(a, dtype):
+      if a is None:
+        return None, None
+      a = np.ascontiguousarray(a, dtype=dtype)
+      return a, _as_ptr(a)
+    k1, a1 = p(pos_x, np.float64)
+    k2, a2 = p(pos_y, np.float64)
+    k3, a3 = p(cursor, np.int32)
+    k4, a4 = p(step_count, np.int32)
+    k5, a5 = p(reset_next, np.uint8)
+    _native.check(self._lib.swb_upload_state(self._h, a1, a2, a3, a4, a5, self._stream()))
+
+  def launch_count(self):
+    return int(self._lib.swb_launch_count(self._h))
+
+
+def fill_task_nodes(cfg, nodes):
+  if not 1 <= len(nodes) <= _native.MAX_NODES:
+    raise ValueError('task tree has %d nodes (max %d)' % (len(nodes), _native.MAX_NODES))
+  cfg.n_nodes = len(nodes)
+  for i, nd in enumerate(nodes):
+    n = cfg.nodes[i]
+    kind = nd['kind']
+    if kind == 'find_goal':
+      n.kind = _native.TASK_FIND_GOAL
+      n.filter_slot = int(nd['filter_slot'])
+      n.goal[0], n.goal[1] = [float(v) for v in nd['goal']]
+      n.weights[0], n.weights[1] = [float(v) for v in nd['weights']]
+      n.terminate_distance = float(nd['terminate_distance'])
+      n.terminate_bonus = float(nd['terminate_bonus'])
+      n.raw_reward_multiplier = float(nd['raw_reward_multiplier'])
+      n.sparse_reward = int(bool(nd['sparse_reward']))
+    elif kind == 'clustering':
+      n.kind = _native.TASK_CLUSTERING
+      slots = nd['cluster_slots']
+      if len(slots) > _native.MAX_CHILDREN:
+        raise ValueError('at most %d clusters' % _native.MAX_CHILDREN)
+      n.n_clusters = len(slots)
+      for j, s in enumerate(slots):
+        n.cluster_slots[j] = int(s)
+      n.termination_threshold = float(nd['termination_threshold'])
+      n.terminate_bonus = float(nd['terminate_bonus'])
+      n.sparse_reward = int(bool(nd['sparse_reward']))
+      n.reward_range = float(nd['reward_range'])
+    elif kind == 'meta':
+      n.kind = _native.TASK_META
+      kids = nd['children']
+      if len(kids) > _native.MAX_CHILDREN:
+        raise ValueError('at most %d subtasks' % _native.MAX_CHILDREN)
+      n.n_children = len(kids)
+      for j, c in enumerate(kids):
+        n.children[j] = int(c)
+      n.aggregator = _native.AGG[nd['aggregator']]
+      n.criterion = _native.CRIT[nd['criterion']]
+      n.terminate_bonus = float(nd['terminate_bonus'])
+    elif kind == 'no_reward':
+      n.kind = _native.TASK_NO_REWARD
+    else:
+      raise ValueError('unknown task node kind %r' % (kind,))
+
+
+SHAPE_IDS = {
+    'triangle': 1, 'square': 2, 'pentagon': 3, 'hexagon': 4, 'octagon': 5, 'circle': 6,
+    'star_4': 7, 'star_5': 8, 'star_6': 9, 'spoke_4': 10, 'spoke_5': 11, 'spoke_6': 12,
+}
+
+
+def fill_shapes(cfg, shapes):
+  for name, sid in SHAPE_IDS.items():
+    v = np.asarray(shapes[name], dtype=np.float64)
+    if v.ndim != 2 or v.shape[1] != 2 or len(v) > _native.MAX_VERTS:
+      raise ValueError('bad vertex table for %s' % name)
+    cfg.shape_n_verts[sid] = len(v)
+    for i in range(len(v)):
+      cfg.shape_verts[sid][i][0] = float(v[i, 0])
+      cfg.shape_verts[sid][i][1] = float(v[i, 1])
