@@ -178,8 +178,12 @@ class Engine(object):
                                        self._stream()))
     return frames
 
-  def step_host(self, actions, raster=None, want_frames=True):
-    """Whole call with HOST buffers (numpy in, numpy out): H2D, step, render, D2H, sync."""
+  def step_host(self, actions, raster=None, want_frames=True, out=None):
+    """Whole call with HOST buffers (numpy in, numpy out): H2D, step, render, D2H, sync.
+
+    `out`: optional dict of preallocated (ideally pinned) numpy arrays reward/step_type/
+    success/status/frames to receive the results.
+    """
     a = np.ascontiguousarray(actions)
     if self.action_kind == _native.ACT_EMBODIED:
       a = np.ascontiguousarray(a, dtype=np.int32)
@@ -190,13 +194,15 @@ class Engine(object):
       a = np.ascontiguousarray(a, dtype=np.float64)
       dt = _native.DTYPE_F64
     E = self.n_envs
-    reward = np.empty(E, np.float64)
-    step_type = np.empty(E, np.int8)
-    success = np.empty(E, np.uint8)
-    status = np.empty(E, np.uint8)
+    out = out or {}
+    reward = out.get('reward') if 'reward' in out else np.empty(E, np.float64)
+    step_type = out.get('step_type') if 'step_type' in out else np.empty(E, np.int8)
+    success = out.get('success') if 'success' in out else np.empty(E, np.uint8)
+    status = out.get('status') if 'status' in out else np.empty(E, np.uint8)
     frames = None
     if raster is not None and want_frames:
-      frames = np.empty((E, raster.height, raster.width, 3), np.uint8)
+      frames = (out.get('frames') if 'frames' in out
+                else np.empty((E, raster.height, raster.width, 3), np.uint8))
     _native.check(self._lib.swb_step_host(
         self._h, raster._h if raster is not None else None, _as_ptr(a), dt, _as_ptr(reward),
         _as_ptr(step_type), _as_ptr(success), _as_ptr(status),

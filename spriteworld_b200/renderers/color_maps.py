@@ -1,0 +1,60 @@
+"""Colour-space conversions for rendering (reference: renderers/color_maps.py:26-28).
+
+`hsv_to_rgb(c)` is the per-sprite callable a PILRenderer takes as `color_to_rgb`;
+`hsv_to_rgb_batch` is its vectorised form used when scenes are sampled in bulk.  Both
+reproduce `colorsys.hsv_to_rgb` followed by `(255 * rgb).astype(uint8)` (truncation),
+evaluated in float32 when the colour factors are NumPy float32 scalars (as sampled by
+`Continuous(..., dtype='float32')`) and in float64 otherwise.
+"""
+import colorsys
+
+import numpy as np
+
+
+def hsv_to_rgb(c):
+  """HSV tuple -> uint8 RGB tuple."""
+  return tuple((255 * np.array(colorsys.hsv_to_rgb(*c))).astype(np.uint8))
+
+
+def _hsv_arrays(h, s, v):
+  """colorsys.hsv_to_rgb on arrays of one float dtype (elementwise IEEE ops, no fusion)."""
+  dt = h.dtype.type
+  one, six = dt(1.0), dt(6.0)
+  h6 = h * six
+  i = h6.astype(np.int64)  # int() truncates
+  f = h6 - i.astype(h.dtype)
+  p = v * (one - s)
+  q = v * (one - s * f)
+  t = v * (one - s * (one - f))
+  i = i % 6
+  r = np.choose(i, [v, q, p, p, t, v])
+  g = np.choose(i, [t, v, v, q, p, p])
+  b = np.choose(i, [p, p, t, v, v, q])
+  grey = s == 0
+  r, g, b = np.where(grey, v, r), np.where(grey, v, g), np.where(grey, v, b)
+  return r, g, b
+
+
+def hsv_to_rgb_batch(c0, c1, c2, is_f32):
+  """Vectorised hsv_to_rgb.
+
+  Args:
+    c0, c1, c2: float64 arrays (values of the colour factors).
+    is_f32: bool array, True where all three factors of the sprite were float32 scalars.
+  Returns:
+    uint8 array shaped c0.shape + (3,).
+  """
+  c0, c1, c2 = (np.asarray(a, np.float64) for a in (c0, c1, c2))
+  is_f32 = np.broadcast_to(np.asarray(is_f32, bool), c0.shape)
+  out = np.zeros(c0.shape + (3,), np.uint8)
+  for f32 in (True, False):
+    sel = is_f32 == f32
+    if not sel.any():
+      continue
+    dt = np.float32 if f32 else np.float64
+    r, g, b = _hsv_arrays(c0[sel].astype(dt), c1[sel].astype(dt), c2[sel].astype(dt))
+    scale = dt(255)
+    out[sel, 0] = (scale * r).astype(np.uint8)
+    out[sel, 1] = (scale * g).astype(np.uint8)
+    out[sel, 2] = (scale * b).astype(np.uint8)
+  return out
