@@ -90,6 +90,8 @@ def load():
   L.swb_upload_scenes.argtypes = [vp, ctypes.POINTER(SceneSoA), vp, vp, ci, vp]
   L.swb_request_reset.argtypes = [vp, vp, vp]
   L.swb_step.argtypes = [vp, vp, ci, ctypes.POINTER(StepOut), vp]
+  L.swb_eval_task.argtypes = [vp, ctypes.POINTER(StepOut), vp]
+  L.swb_apply_action.argtypes = [vp, vp, ci, ctypes.POINTER(StepOut), vp]
   L.swb_raster_create.argtypes = [vp, ci, ci, ci, vp, ctypes.POINTER(vp)]
   L.swb_raster_destroy.argtypes = [vp]
   L.swb_raster_destroy.restype = None
@@ -113,7 +115,7 @@ def load():
 EXPORTS = (
     'swb_last_error', 'swb_version', 'swb_sizeof_config', 'swb_sizeof_task_node',
     'swb_engine_create', 'swb_engine_destroy', 'swb_upload_scenes', 'swb_request_reset',
-    'swb_step', 'swb_raster_create', 'swb_raster_destroy', 'swb_render', 'swb_step_render',
+    'swb_step', 'swb_eval_task', 'swb_apply_action', 'swb_raster_create', 'swb_raster_destroy', 'swb_render', 'swb_step_render',
     'swb_step_host', 'swb_state_pointers', 'swb_download_state', 'swb_upload_state',
     'swb_launch_count')
 

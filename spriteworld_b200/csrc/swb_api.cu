@@ -323,10 +323,39 @@ int swb_step(swb_engine *eng, const void *actions, int32_t action_dtype, const s
   if (ensure_step_cfg(eng)) return 1;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int blocks = (eng->st.E + STEP_WARPS - 1) / STEP_WARPS;
-  step_kernel<<<blocks, STEP_WARPS * 32, 0, stream>>>(eng->st, actions, action_dtype, *out);
+  step_kernel<<<blocks, STEP_WARPS * 32, 0, stream>>>(eng->st, actions, action_dtype, *out, 0);
   eng->launches++;
   CUDA_TRY(cudaGetLastError());
   return 0;
+}
+
+static int launch_partial(swb_engine *eng, const void *actions, int32_t action_dtype,
+                          const swb_step_out *out, void *stream_, int mode) {
+  if (!eng || !out) return fail("null argument");
+  if (!out->reward || !out->step_type || !out->success || !out->status)
+    return fail("every swb_step_out pointer must be set");
+  CUDA_TRY(cudaSetDevice(eng->device));
+  if (ensure_step_cfg(eng)) return 1;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int blocks = (eng->st.E + STEP_WARPS - 1) / STEP_WARPS;
+  step_kernel<<<blocks, STEP_WARPS * 32, 0, stream>>>(eng->st, actions, action_dtype, *out, mode);
+  eng->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int swb_eval_task(swb_engine *eng, const swb_step_out *out, void *stream) {
+  return launch_partial(eng, nullptr, SWB_DTYPE_F32, out, stream, 1);
+}
+
+int swb_apply_action(swb_engine *eng, const void *actions, int32_t action_dtype,
+                     const swb_step_out *out, void *stream) {
+  if (!actions) return fail("swb_apply_action: null actions");
+  const bool emb = eng && eng->cfg.action_kind == SWB_ACT_EMBODIED;
+  if (emb && action_dtype != SWB_DTYPE_I32) return fail("Embodied actions must be int32 [E][2]");
+  if (!emb && action_dtype != SWB_DTYPE_F32 && action_dtype != SWB_DTYPE_F64)
+    return fail("SelectMove/DragAndDrop actions must be float32 or float64 [E][4]");
+  return launch_partial(eng, actions, action_dtype, out, stream, 2);
 }
 
 int swb_raster_create(swb_engine *eng, int32_t width, int32_t height, int32_t aa,

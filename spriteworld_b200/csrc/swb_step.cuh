@@ -325,14 +325,17 @@ __device__ void task_eval(const WarpSprites &ws, int S, double *reward, int *suc
 }
 
 __global__ void __launch_bounds__(STEP_WARPS * 32)
-step_kernel(DevState st, const void *__restrict__ actions, int action_dtype, swb_step_out out) {
+step_kernel(DevState st, const void *__restrict__ actions, int action_dtype, swb_step_out out,
+            int mode) {
+  // mode 0: Environment.step; 1: task.reward/success of the live state only;
+  // 2: action_space.step only (no velocity update, task or counters)
   __shared__ WarpSprites s_ws[STEP_WARPS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int e = blockIdx.x * STEP_WARPS + warp;
   if (e >= st.E) return;
   WarpSprites &ws = s_ws[warp];
   const int S = st.S;
-  const bool resetting = st.reset_next[e] != 0;
+  const bool resetting = mode == 0 && st.reset_next[e] != 0;
   int cursor = st.cursor[e];
   if (resetting) cursor = (cursor + 1) % st.K;  // environment.py:90-91 -> reset() :74-78
   const int scene0 = (e * st.K + cursor) * S;
@@ -356,7 +359,7 @@ step_kernel(DevState st, const void *__restrict__ actions, int action_dtype, swb
   double cost = 0.;
   int status = 0;
   const bool keep = c_step.keep_in_frame != 0;
-  if (!resetting) {
+  if (!resetting && mode != 1) {
     if (c_step.action_kind == SWB_ACT_EMBODIED) {  // action_spaces.py:187-214
       const int32_t *a = reinterpret_cast<const int32_t *>(actions) + 2 * (size_t)e;
       const bool carry = a[0] != 0;
@@ -426,18 +429,34 @@ step_kernel(DevState st, const void *__restrict__ actions, int action_dtype, swb
     }
     __syncwarp();
     // velocity update of every sprite (environment.py:98-99)
-    if (lane < S && ws.shape[lane]) sprite_move(ws, lane, vx, vy, keep);
+    if (mode == 0 && lane < S && ws.shape[lane]) sprite_move(ws, lane, vx, vy, keep);
     __syncwarp();
   }
 
-  if (lane < S) {
+  if (mode != 1 && lane < S) {
     st.pos_x[e * S + lane] = ws.x[lane];
     st.pos_y[e * S + lane] = ws.y[lane];
+  }
+  if (mode == 2) {
+    if (lane == 0) {
+      out.reward[e] = cost;
+      out.step_type[e] = (int8_t)SWB_STEP_MID;
+      out.success[e] = 0;
+      out.status[e] = (uint8_t)status;
+    }
+    return;
   }
   if (lane == 0) {
     double tr;
     int succ;
     task_eval(ws, S, &tr, &succ, &status);
+    if (mode == 1) {
+      out.reward[e] = tr;
+      out.step_type[e] = (int8_t)SWB_STEP_MID;
+      out.success[e] = (uint8_t)succ;
+      out.status[e] = (uint8_t)status;
+      return;
+    }
     int step_type;
     int count = st.step_count[e];
     if (resetting) {

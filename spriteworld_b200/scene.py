@@ -75,3 +75,120 @@ def batch_from_factor_arrays(x, y, pos_f32, shape, angle, scale, c0, c1, c2, vx,
   b['factors'][..., 0], b['factors'][..., 1] = scale, angle
   b['factors'][..., 2], b['factors'][..., 3], b['factors'][..., 4] = c0, c1, c2
   return b
+
+
+# ---------------------------------------------------------------------------------
+# SceneLayout (sprite_generators.py) -> scene arrays
+# ---------------------------------------------------------------------------------
+
+_DEFAULTS = dict(x=0.5, y=0.5, shape='square', angle=0, scale=0.1, c0=0, c1=0, c2=0,
+                 x_vel=0.0, y_vel=0.0)   # Sprite.__init__ defaults (sprite.py:56-66)
+
+
+def _full_columns(table):
+  """The ten factor columns of a SpriteTable, defaults filled in, typed like
+  `Sprite.factors` would type them (positions are float32 only if x and y both are)."""
+  from spriteworld_b200.factor_distributions import _as_column
+  cols = {}
+  for name, default in _DEFAULTS.items():
+    col = table.columns.get(name)
+    cols[name] = _as_column([default] * table.rows) if col is None else col
+  x, y = cols['x'], cols['y']
+  if not (x.dtype == np.float32 and y.dtype == np.float32):
+    # np.array([x, y]) promotes: anything that is not float32 + float32 becomes float64
+    if x.dtype != object:
+      cols['x'] = x.astype(np.float64)
+    if y.dtype != object:
+      cols['y'] = y.astype(np.float64)
+  return cols
+
+
+def _numeric(col):
+  if col.dtype == object:
+    return np.array([float(v) for v in col], np.float64)
+  return col.astype(np.float64)
+
+
+def _is_f32(col):
+  if col.dtype == object:
+    return np.array([isinstance(v, np.float32) for v in col], bool)
+  return np.full(len(col), col.dtype == np.float32, bool)
+
+
+def _shape_ids(col):
+  from spriteworld_b200 import constants
+  if col.dtype != object and np.issubdtype(col.dtype, np.integer):
+    return col.astype(np.uint8)
+  return np.array([int(constants.ShapeType[str(v)]) for v in col], np.uint8)
+
+
+def _table_rgb(cols, color_to_rgb):
+  from spriteworld_b200.renderers import color_maps
+  c = [cols['c0'], cols['c1'], cols['c2']]
+  rows = len(c[0])
+  if color_to_rgb is None:   # colours are already RGB (pil_renderer.py:53-55)
+    return np.stack([_numeric(a).astype(np.int64) for a in c], -1).astype(np.uint8)
+  homogeneous = all(a.dtype != object for a in c) and len({a.dtype for a in c}) == 1
+  if color_to_rgb is color_maps.hsv_to_rgb and homogeneous and c[0].dtype in (
+      np.dtype(np.float32), np.dtype(np.float64)):
+    return color_maps.hsv_to_rgb_batch(_numeric(c[0]), _numeric(c[1]), _numeric(c[2]),
+                                       c[0].dtype == np.float32)
+  out = np.zeros((rows, 3), np.uint8)   # arbitrary callable or mixed scalar types
+  for i in range(rows):
+    out[i] = [int(v) for v in color_to_rgb((c[0][i], c[1][i], c[2][i]))]
+  return out
+
+
+def arrays_from_layout(layout, n_slots, filters=(), color_to_rgb=None):
+  """SceneLayout -> scene batch (n, n_slots), sprites right-aligned (empty slots first).
+
+  Args:
+    layout: sprite_generators.SceneLayout.
+    n_slots: sprite slots per env.
+    filters: task filter distributions; bit i of `member` = filters[i].contains(sprite).
+    color_to_rgb: the PILRenderer's colour map (None, color_maps.hsv_to_rgb or a callable).
+  """
+  if layout.n and int(layout.count.max()) > n_slots:
+    raise ValueError('a scene has %d sprites but the engine has %d slots'
+                     % (int(layout.count.max()), n_slots))
+  per_table = []
+  for table in layout.tables:
+    if table.rows == 0:
+      per_table.append(None)
+      continue
+    cols = _full_columns(table)
+    member = np.zeros(table.rows, np.uint32)
+    for bit, f in enumerate(filters):
+      member |= np.asarray(f.contains_batch(cols), bool).astype(np.uint32) << np.uint32(bit)
+    if '_transform' in table.columns:
+      m = table.columns['_transform']
+    else:
+      m = transform_matrices(_numeric(cols['scale']), _numeric(cols['angle']))
+    pos_f32 = table.columns.get('_pos_f32')
+    if pos_f32 is None:
+      pos_f32 = _is_f32(cols['x']) & _is_f32(cols['y'])
+    per_table.append(dict(
+        x=_numeric(cols['x']), y=_numeric(cols['y']), m=m, vx=_numeric(cols['x_vel']),
+        vy=_numeric(cols['y_vel']), member=member, shape=_shape_ids(cols['shape']),
+        pos_f32=pos_f32.astype(np.uint8), rgb=_table_rgb(cols, color_to_rgb),
+        factors=np.stack([_numeric(cols[k]) for k in ('scale', 'angle', 'c0', 'c1', 'c2')],
+                         -1).astype(np.float32)))
+  n = layout.n
+  b = empty_batch(n, n_slots)
+  valid = layout.valid()
+  scene_i, slot_j = np.nonzero(valid)
+  dst = n_slots - layout.count[scene_i] + slot_j
+  tab, row = layout.ref_table[valid], layout.ref_row[valid]
+  for t, data in enumerate(per_table):
+    if data is None:
+      continue
+    sel = tab == t
+    si, di, ri = scene_i[sel], dst[sel], row[sel]
+    b['x'][si, di], b['y'][si, di] = data['x'][ri], data['y'][ri]
+    for k, f in enumerate(('m00', 'm01', 'm10', 'm11')):
+      b[f][si, di] = data['m'][ri, k]
+    b['vx'][si, di], b['vy'][si, di] = data['vx'][ri], data['vy'][ri]
+    b['member'][si, di], b['shape'][si, di] = data['member'][ri], data['shape'][ri]
+    b['pos_f32'][si, di], b['rgb'][si, di] = data['pos_f32'][ri], data['rgb'][ri]
+    b['factors'][si, di] = data['factors'][ri]
+  return b
