@@ -379,6 +379,8 @@ int swb_raster_create(swb_engine *eng, int32_t width, int32_t height, int32_t aa
   rd.band_rows = height <= 64 ? height : 64;
   rd.n_bands = (height + rd.band_rows - 1) / rd.band_rows;
   rd.max_spans = 1;
+  rd.ncls_x = r->ax.n_cls;
+  rd.ncls_y = r->ay.n_cls;
   int rows = 0;
   for (int b = 0; b < rd.n_bands; ++b) {
     const int y0 = b * rd.band_rows, y1 = std::min(y0 + rd.band_rows, height) - 1;
@@ -404,7 +406,11 @@ static int launch_render(swb_engine *eng, swb_raster *r, uint8_t *frames, uint8_
   if (r->eng != eng) return fail("raster belongs to another engine");
   RasterDev rd = r->rd;
   rd.max_spans = eng->max_spans;
-  const RenderLayout L(eng->st.S, r->smem_rows, rd.max_spans, rd.band_rows, rd.W, rd.aa);
+  const RenderLayout L(eng->st.S, r->smem_rows, rd.max_spans, rd.band_rows, rd.W, rd.aa, rd.ncls_x,
+                       rd.ncls_y);
+  if (L.list_rows < r->smem_rows)
+    return fail("render scratch holds %d crossing lists but a sprite may span %d canvas rows", L.list_rows,
+                r->smem_rows);
   int max_smem = 0;
   CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, eng->device));
   if (L.total > max_smem)

@@ -62,6 +62,7 @@ struct RasterDev {
   int band_rows;  // output rows per CTA
   int n_bands;
   int max_spans;  // spans kept per (sprite, canvas row)
+  int ncls_x, ncls_y;  // distinct tap vectors per axis
   AxisTables ax, ay;
 };
 

@@ -4,17 +4,21 @@
 // ever materialised; the CTA works on what Pillow's two stages are functions of:
 //
 //   A  vertices   int(canvas * (R.S.v + pos)) in fp64 (sprite.py:128-133, pil_renderer.py:81,
-//                 Pillow's (int) truncation), then Pillow's edge records (float32 dx).
-//   B  spans      per (sprite, canvas row): Pillow's scan conversion (sorted float32 edge
-//                 crossings, ROUND_UP/ROUND_DOWN span ends, duplicated end points, the
-//                 corner-joining refinement, horizontal edges) -> <= M [xs, xe] spans.
+//                 Pillow's (int) truncation), then Pillow's edge records (float32 dx) and,
+//                 per edge, the value Pillow's corner-joining refinement would overwrite
+//                 its crossing with on its first row / on the polygon's last row.
+//   B  spans      Pillow's scan conversion.  B1 is edge-parallel: every edge drops its
+//                 float32 crossing (twice where it ends on an interior row) into the
+//                 crossing list of each canvas row it spans.  B2 is row-parallel: sort the
+//                 list, pair it up with Pillow's ROUND_UP/ROUND_DOWN rule, add horizontal
+//                 edges -> <= M merged [xs, xe] spans per (sprite, row).
 //   C  per sprite region (the outputs whose 2-D tap window can see the sprite), in tiles
 //      of 16x16 outputs:
-//        H  horizontal LANCZOS pass of the canvas rows the tile needs.  A canvas row is
-//           piecewise constant, so an output is  bg*K + sum_runs (colour-bg) * (P[b]-P[a])
-//           with P the prefix sums of the 22-bit tap vector; occlusion is resolved front
-//           to back with a <=32-bit coverage mask of the tap window.  Result clip8'ed to
-//           uint8 exactly like Pillow's intermediate image.
+//        H  horizontal LANCZOS pass of the canvas rows the tile needs, one half-warp per
+//           canvas row.  A canvas row is piecewise constant, so an output is
+//           bg*K + sum_runs (colour-bg) * (P[b]-P[a]) with P the prefix sums of the
+//           22-bit tap vector; occlusion is resolved front to back with a <=32-bit
+//           coverage mask of the tap window.  clip8'ed like Pillow's uint8 intermediate.
 //        V  vertical pass over the tile's H values (paired taps: equal coefficients share
 //           one multiply), clip8, written into the frame staged in shared memory.
 //   D  the staged frame (background + tiles) goes to HBM as 128-bit stores, rows flipped
@@ -32,31 +36,39 @@ namespace swb {
 constexpr int R_THREADS = 256;
 constexpr int TILE_Y = 16;
 constexpr int TILE_X = 16;
-constexpr int MAX_CROSS = 40;   // edge crossings kept per (sprite, row)
 constexpr int MAX_ROW_SPANS = 12;
+constexpr int EV = SWB_MAX_VERTS;  // edge slots per sprite
 
 struct RenderLayout {
-  int S, rows, M, band_rows, W, aa;
-  int off_pos, off_meta, off_iv, off_edge_i, off_edge_f, off_edge_flag, off_region;
-  int off_rowmask, off_spans, off_htile, off_frame, total;
-  int ht_rows;
-  __host__ __device__ RenderLayout(int S_, int rows_, int M_, int band_rows_, int W_, int aa_)
-      : S(S_), rows(rows_), M(M_), band_rows(band_rows_), W(W_), aa(aa_) {
+  int S, rows, M, band_rows, W, aa, ncx, ncy, cap;
+  int off_pos, off_meta, off_iv, off_edge_i, off_edge_f, off_edge_b, off_hl, off_region;
+  int off_rowmask, off_spans, off_prefix, off_prog, off_scratch, off_frame, total;
+  int ht_rows, scratch_bytes, list_rows;
+  __host__ __device__ RenderLayout(int S_, int rows_, int M_, int band_rows_, int W_, int aa_,
+                                   int ncx_, int ncy_)
+      : S(S_), rows(rows_), M(M_), band_rows(band_rows_), W(W_), aa(aa_), ncx(ncx_), ncy(ncy_) {
     int o = 0;
     auto take = [&](int bytes) { int r = o; o += (bytes + 15) & ~15; return r; };
     off_pos = take(S * 6 * 8);
-    off_meta = take(S * 12 * 4);
-    off_iv = take(S * SWB_MAX_VERTS * 2 * 4);
-    off_edge_i = take(S * SWB_MAX_VERTS * 4 * 4);
-    off_edge_f = take(S * SWB_MAX_VERTS * 4);
-    off_edge_flag = take(S * SWB_MAX_VERTS);
+    off_meta = take(S * 14 * 4);
+    off_iv = take(S * EV * 2 * 4);
+    off_edge_i = take(S * EV * 4 * 4);     // x0, y0, ymin, ymax
+    off_edge_f = take(S * EV * 5 * 4);     // dx, ovs, ove, join nv (start), join nv (end)
+    off_edge_b = take(S * EV * 3);         // flag, join partner (start), join partner (end)
+    off_hl = take(S * EV * 3 * 2);         // horizontal edges: y, xmin, xmax (int16)
     off_region = take(S * 4 * 2);
     off_rowmask = take(rows * 4);
     off_spans = take(S * rows * M * 4);
+    off_prefix = take(ncx * 33 * 4);
+    off_prog = take(ncy * PROG_STRIDE * 4);
     ht_rows = TILE_Y * aa + 32;
-    off_htile = take(ht_rows * TILE_X * 8);
+    // scratch: H tile + staged frame; phase B aliases it with the per-row crossing lists
+    off_scratch = take(ht_rows * TILE_X * 8);
     off_frame = take(band_rows * W * 3);
     total = o;
+    scratch_bytes = total - off_scratch;
+    cap = (M > 1) ? 16 : 8;                // crossings kept per (sprite, row)
+    list_rows = scratch_bytes / (cap * 4 + 4);
   }
 };
 
@@ -97,82 +109,6 @@ __device__ __forceinline__ void add_span(int *lxs, int *lxe, int &n, int xs, int
   }
 }
 
-// Pillow polygon_generic for one canvas row of one sprite.  Returns the number of spans.
-__device__ int scan_row(const int *ex0, const int *ey0, const int *eymin, const int *eymax,
-                        const float *edx, const uint8_t *eflag, int ne, int y, int p_ymax,
-                        int CW, int *lxs, int *lxe, bool &ovf) {
-  float xx[MAX_CROSS];
-  int j = 0;
-  int n = 0;
-  for (int i = 0; i < ne; ++i) {
-    const int fl = eflag[i];
-    if (fl == 1) {  // horizontal edge: drawn directly as hline(xmin, y, xmax)
-      if (ey0[i] == y) {
-        int xs = max(eymin[i], 0), xe = min(eymax[i], CW - 1);  // (xmin,xmax stored here)
-        if (xs <= xe) add_span(lxs, lxe, n, xs, xe, ovf);
-      }
-      continue;
-    }
-    if (fl != 2) continue;
-    if (y < eymin[i] || y > eymax[i]) continue;
-    const float dx = edx[i];
-    const float x = edge_x_at(y, ey0[i], dx, ex0[i]);
-    if (j < MAX_CROSS) xx[j] = x; else ovf = true;
-    ++j;
-    if (y == eymax[i] && y < p_ymax) {
-      if (j < MAX_CROSS) xx[j] = x; else ovf = true;
-      ++j;
-    } else if (dx != 0.0f) {
-      const bool cur_start = (y == eymin[i]);
-      const bool cur_end_last = (y == p_ymax && y == eymax[i]);
-      if (cur_start || cur_end_last) {
-        int xi = 0;
-        for (int k = 0; k < i; ++k) {
-          if (eflag[k] != 2) continue;
-          const int my = xi;
-          if (y >= eymin[k] && y <= eymax[k]) xi += (y == eymax[k] && y < p_ymax) ? 2 : 1;
-          const float odx = edx[k];
-          if ((dx > 0.0f && odx <= 0.0f) || (dx < 0.0f && odx >= 0.0f)) continue;
-          const bool both_start = cur_start && (y == eymin[k]);
-          const bool both_end = cur_end_last && (y == eymax[k]);
-          if (!both_start && !both_end) continue;
-          const float ox = edge_x_at(y, ey0[k], odx, ex0[k]);
-          if (roundf(x) != roundf(ox)) continue;
-          const int off = (y == p_ymax) ? -1 : 1;
-          const float adj = edge_x_at(y + off, ey0[i], dx, ex0[i]);
-          const float adjo = edge_x_at(y + off, ey0[k], odx, ex0[k]);
-          const bool right = (y == eymax[i]) ? (dx < 0.0f) : (dx > 0.0f);
-          float nv = right ? __fsub_rn(fminf(adj, adjo), 1.0f) : __fadd_rn(fmaxf(adj, adjo), 1.0f);
-          nv = floorf(__fadd_rn(nv, 0.5f));
-          nv = right ? fmaxf(nv, x) : fminf(nv, x);
-          if (my < MAX_CROSS) xx[my] = nv;
-          break;
-        }
-      }
-    }
-  }
-  if (j > MAX_CROSS) j = MAX_CROSS;
-  for (int a = 1; a < j; ++a) {  // insertion sort, ascending
-    float v = xx[a];
-    int b = a - 1;
-    while (b >= 0 && xx[b] > v) { xx[b + 1] = xx[b]; --b; }
-    xx[b + 1] = v;
-  }
-  int x_pos = 0;
-  for (int i = 1; i < j; i += 2) {
-    const int x_end = round_down_f(xx[i]);
-    if (x_end < x_pos) continue;
-    if (xx[i - 1] > (float)x_pos) {
-      x_pos = round_up_f(xx[i - 1]);
-      if (x_end < x_pos) continue;
-    }
-    int xs = max(x_pos, 0), xe = min(x_end, CW - 1);
-    if (xs <= xe) add_span(lxs, lxe, n, xs, xe, ovf);
-    x_pos = x_end + 1;
-  }
-  return n;
-}
-
 __global__ void __launch_bounds__(R_THREADS)
 render_kernel(DevState st, RasterDev rd, uint8_t *__restrict__ frames, int smem_rows) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -180,7 +116,7 @@ render_kernel(DevState st, RasterDev rd, uint8_t *__restrict__ frames, int smem_
   const int band = blockIdx.y;
   const int tid = threadIdx.x;
   const int S = st.S;
-  const RenderLayout L(S, smem_rows, rd.max_spans, rd.band_rows, rd.W, rd.aa);
+  const RenderLayout L(S, smem_rows, rd.max_spans, rd.band_rows, rd.W, rd.aa, rd.ncls_x, rd.ncls_y);
   const int M = rd.max_spans;
 
   double *s_px = reinterpret_cast<double *>(smem + L.off_pos);
@@ -189,21 +125,30 @@ render_kernel(DevState st, RasterDev rd, uint8_t *__restrict__ frames, int smem_
   int *s_nv = reinterpret_cast<int *>(smem + L.off_meta);
   int *s_rgb = s_nv + S;
   int *s_xmin = s_rgb + S, *s_xmax = s_xmin + S, *s_gymin = s_xmax + S, *s_gymax = s_gymin + S;
-  int *s_pymin = s_gymax + S, *s_pymax = s_pymin + S, *s_ne = s_pymax + S, *s_shape = s_ne + S;
-  int *s_r0 = s_shape + S, *s_rcnt = s_r0 + S;
+  int *s_pymin = s_gymax + S, *s_pymax = s_pymin + S, *s_shape = s_pymax + S;
+  int *s_r0 = s_shape + S, *s_rcnt = s_r0 + S, *s_nh = s_rcnt + S, *s_roff = s_nh + S;
   int *s_ivx = reinterpret_cast<int *>(smem + L.off_iv);
-  int *s_ivy = s_ivx + S * SWB_MAX_VERTS;
+  int *s_ivy = s_ivx + S * EV;
   int *e_x0 = reinterpret_cast<int *>(smem + L.off_edge_i);
-  int *e_y0 = e_x0 + S * SWB_MAX_VERTS;
-  int *e_ymin = e_y0 + S * SWB_MAX_VERTS;
-  int *e_ymax = e_ymin + S * SWB_MAX_VERTS;
+  int *e_y0 = e_x0 + S * EV, *e_ymin = e_y0 + S * EV, *e_ymax = e_ymin + S * EV;
   float *e_dx = reinterpret_cast<float *>(smem + L.off_edge_f);
-  uint8_t *e_flag = smem + L.off_edge_flag;
+  float *e_ovs = e_dx + S * EV, *e_ove = e_ovs + S * EV;
+  float *e_jvs = e_ove + S * EV, *e_jve = e_jvs + S * EV;
+  uint8_t *e_flag = smem + L.off_edge_b;
+  int8_t *e_jks = reinterpret_cast<int8_t *>(e_flag + S * EV);
+  int8_t *e_jke = e_jks + S * EV;
+  short *s_hl = reinterpret_cast<short *>(smem + L.off_hl);  // [S][EV][3]
   short *s_region = reinterpret_cast<short *>(smem + L.off_region);  // [S][4] yo0,yo1,xo0,xo1
   uint32_t *s_rowmask = reinterpret_cast<uint32_t *>(smem + L.off_rowmask);
   uint32_t *s_spans = reinterpret_cast<uint32_t *>(smem + L.off_spans);
-  uint2 *s_ht = reinterpret_cast<uint2 *>(smem + L.off_htile);
+  int32_t *s_prefix = reinterpret_cast<int32_t *>(smem + L.off_prefix);
+  int32_t *s_prog = reinterpret_cast<int32_t *>(smem + L.off_prog);
+  uint2 *s_ht = reinterpret_cast<uint2 *>(smem + L.off_scratch);
   uint8_t *s_frame = smem + L.off_frame;
+  // phase-B view of the scratch area: per-row crossing lists
+  const int CAP = L.cap;
+  int *s_lcnt = reinterpret_cast<int *>(smem + L.off_scratch);
+  float *s_list = reinterpret_cast<float *>(smem + L.off_scratch) + L.list_rows;
   __shared__ int s_overflow;
 
   const int yo_b0 = band * rd.band_rows;
@@ -214,7 +159,7 @@ render_kernel(DevState st, RasterDev rd, uint8_t *__restrict__ frames, int smem_
   const int row_b1 = rd.ay.win_min[yo_b1 - 1] + rd.ay.win_len[yo_b1 - 1];  // exclusive
   const int n_rows = row_b1 - row_b0;
 
-  // ---- phase 0: sprite records of this env's current scene ---------------------
+  // ---- phase 0: sprite records of this env's current scene, tables -------------------
   if (tid == 0) s_overflow = 0;
   if (tid < S) {
     const int scene = (e * st.K + st.cursor[e]) * S + tid;
@@ -228,29 +173,19 @@ render_kernel(DevState st, RasterDev rd, uint8_t *__restrict__ frames, int smem_
     s_m[1 * S + tid] = st.p_m01[scene];
     s_m[2 * S + tid] = st.p_m10[scene];
     s_m[3 * S + tid] = st.p_m11[scene];
+    s_nh[tid] = 0;
   }
+  for (int i = tid; i < rd.ncls_x * 33; i += R_THREADS) s_prefix[i] = rd.ax.prefix[i];
+  for (int i = tid; i < rd.ncls_y * PROG_STRIDE; i += R_THREADS) s_prog[i] = rd.ay.program[i];
   for (int i = tid; i < n_rows; i += R_THREADS) s_rowmask[i] = 0u;
   for (int i = tid; i < S * n_rows * M; i += R_THREADS) s_spans[i] = 0x0000FFFFu;  // xs > xe
-  {  // background fill of the staged frame
-    const uint32_t r = rd.bg & 255u, g = (rd.bg >> 8) & 255u, b = (rd.bg >> 16) & 255u;
-    const int n_bytes = n_yo * rd.W * 3;
-    if ((rd.bg & 0xFFFFFFu) == 0u || (r == g && g == b)) {
-      const uint32_t w = r * 0x01010101u;
-      uint32_t *f32 = reinterpret_cast<uint32_t *>(s_frame);
-      for (int i = tid; i < (n_bytes + 3) / 4; i += R_THREADS) f32[i] = w;
-    } else {
-      for (int i = tid; i < n_yo * rd.W; i += R_THREADS) {
-        s_frame[3 * i] = (uint8_t)r; s_frame[3 * i + 1] = (uint8_t)g; s_frame[3 * i + 2] = (uint8_t)b;
-      }
-    }
-  }
   __syncthreads();
 
   // ---- phase A1: integer canvas vertices ----------------------------------------
-  for (int t = tid; t < S * SWB_MAX_VERTS; t += R_THREADS) {
-    const int s = t / SWB_MAX_VERTS, i = t % SWB_MAX_VERTS;
+  for (int t = tid; t < S * EV; t += R_THREADS) {
+    const int s = t / EV, i = t % EV;
     if (i < s_nv[s]) {
-      const double *v = st.shape_verts + ((size_t)s_shape[s] * SWB_MAX_VERTS + i) * 2;
+      const double *v = st.shape_verts + ((size_t)s_shape[s] * EV + i) * 2;
       const double vx = v[0], vy = v[1];
       // centred path (sprite.py:96-101): (a*x + c*y) + 0 ; world (sprite.py:128-133): + pos
       const double cx = __dadd_rn(__dadd_rn(__dmul_rn(s_m[0 * S + s], vx), __dmul_rn(s_m[1 * S + s], vy)), 0.0);
@@ -264,24 +199,29 @@ render_kernel(DevState st, RasterDev rd, uint8_t *__restrict__ frames, int smem_
   __syncthreads();
 
   // ---- phase A2: edge records (Pillow add_edge) + per-sprite extents -------------
-  for (int t = tid; t < S * SWB_MAX_VERTS; t += R_THREADS) {
-    const int s = t / SWB_MAX_VERTS, i = t % SWB_MAX_VERTS;
+  for (int t = tid; t < S * EV; t += R_THREADS) {
+    const int s = t / EV, i = t % EV;
     const int nv = s_nv[s];
     int flag = 0;
     if (i < nv) {
       const int j = (i + 1 == nv) ? 0 : i + 1;
-      const int x0 = s_ivx[s * SWB_MAX_VERTS + i], y0 = s_ivy[s * SWB_MAX_VERTS + i];
-      const int x1 = s_ivx[s * SWB_MAX_VERTS + j], y1 = s_ivy[s * SWB_MAX_VERTS + j];
+      const int x0 = s_ivx[s * EV + i], y0 = s_ivy[s * EV + i];
+      const int x1 = s_ivx[s * EV + j], y1 = s_ivy[s * EV + j];
       // the closing edge exists only if the last vertex differs from the first
       const bool exists = (i + 1 < nv) || (x0 != x1 || y0 != y1);
       if (exists) {
         e_x0[t] = x0;
         e_y0[t] = y0;
-        if (y0 == y1) {
+        if (y0 == y1) {  // horizontal: drawn directly as hline(xmin, y, xmax)
           flag = 1;
-          e_ymin[t] = min(x0, x1);  // horizontal edges keep (xmin, xmax) here
-          e_ymax[t] = max(x0, x1);
-          e_dx[t] = 0.0f;
+          if (y0 >= 0 && y0 < rd.CH) {
+            const int xs = max(min(x0, x1), 0), xe = min(max(x0, x1), rd.CW - 1);
+            if (xs <= xe) {
+              const int slot = atomicAdd(&s_nh[s], 1);
+              short *h = s_hl + ((size_t)s * EV + slot) * 3;
+              h[0] = (short)y0; h[1] = (short)xs; h[2] = (short)xe;
+            }
+          }
         } else {
           flag = 2;
           e_ymin[t] = min(y0, y1);
@@ -291,12 +231,16 @@ render_kernel(DevState st, RasterDev rd, uint8_t *__restrict__ frames, int smem_
       }
     }
     e_flag[t] = (uint8_t)flag;
+    e_ovs[t] = nanf("");
+    e_ove[t] = nanf("");
+    e_jks[t] = -1;
+    e_jke[t] = -1;
   }
   if (tid < S) {
     const int nv = s_nv[tid];
     int xmn = INT_MAX, xmx = INT_MIN, ymn = INT_MAX, ymx = INT_MIN;
     for (int i = 0; i < nv; ++i) {
-      const int x = s_ivx[tid * SWB_MAX_VERTS + i], y = s_ivy[tid * SWB_MAX_VERTS + i];
+      const int x = s_ivx[tid * EV + i], y = s_ivy[tid * EV + i];
       xmn = min(xmn, x); xmx = max(xmx, x); ymn = min(ymn, y); ymx = max(ymx, y);
     }
     s_xmin[tid] = xmn; s_xmax[tid] = xmx; s_gymin[tid] = ymn; s_gymax[tid] = ymx;
@@ -305,7 +249,6 @@ render_kernel(DevState st, RasterDev rd, uint8_t *__restrict__ frames, int smem_
     pymin = max(pymin, 0);
     pymax = min(pymax, rd.CH);
     s_pymin[tid] = pymin; s_pymax[tid] = pymax;
-    s_ne[tid] = nv;
     {
       const int r0 = max(pymin, row_b0), r1 = min(min(pymax, rd.CH - 1), row_b1 - 1);
       s_r0[tid] = r0;
@@ -325,30 +268,160 @@ render_kernel(DevState st, RasterDev rd, uint8_t *__restrict__ frames, int smem_
   }
   __syncthreads();
 
-  // ---- phase B: spans per (sprite, canvas row) -----------------------------------
-  {
-    int total = 0;
-    for (int s = 0; s < S; ++s) total += s_rcnt[s];
-    for (int t = tid; t < total; t += R_THREADS) {
-      int s = 0, rem = t;
+  // ---- phase A3: corner joins ("connect discontiguous corners") ---------------------
+  // Edge i and the FIRST earlier edge k that leaves the same corner in the same x
+  // direction -- both starting on row y, or both ending on the polygon's last row --
+  // move k's crossing on that row towards the adjacent row's span (oracle/
+  // sw_raster_oracle.c).  Found per edge here, applied in B1.
+  for (int t = tid; t < S * EV; t += R_THREADS) {
+    if (e_flag[t] != 2) continue;
+    const float dx = e_dx[t];
+    if (dx == 0.0f) continue;
+    const int s = t / EV, i = t % EV, base = s * EV;
+    const int p_ymax = s_pymax[s];
+    for (int pass = 0; pass < 2; ++pass) {
+      const int y = pass == 0 ? e_ymin[t] : p_ymax;
+      if (pass == 1 && e_ymax[t] != p_ymax) break;
+      if (y < 0 || y >= rd.CH) continue;
+      const float x = edge_x_at(y, e_y0[t], dx, e_x0[t]);
+      for (int k = 0; k < i; ++k) {
+        const int u = base + k;
+        if (e_flag[u] != 2) continue;
+        const float odx = e_dx[u];
+        if ((dx > 0.0f && odx <= 0.0f) || (dx < 0.0f && odx >= 0.0f)) continue;
+        if ((pass == 0 ? e_ymin[u] : e_ymax[u]) != y) continue;
+        const float ox = edge_x_at(y, e_y0[u], odx, e_x0[u]);
+        if (roundf(x) != roundf(ox)) continue;
+        const int off = (y == p_ymax) ? -1 : 1;
+        const float adj = edge_x_at(y + off, e_y0[t], dx, e_x0[t]);
+        const float adjo = edge_x_at(y + off, e_y0[u], odx, e_x0[u]);
+        const bool right = (y == e_ymax[t]) ? (dx < 0.0f) : (dx > 0.0f);
+        float nv = right ? __fsub_rn(fminf(adj, adjo), 1.0f) : __fadd_rn(fmaxf(adj, adjo), 1.0f);
+        nv = floorf(__fadd_rn(nv, 0.5f));
+        nv = right ? fmaxf(nv, x) : fminf(nv, x);
+        if (pass == 0) { e_jks[t] = (int8_t)k; e_jvs[t] = nv; }
+        else { e_jke[t] = (int8_t)k; e_jve[t] = nv; }
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  for (int t = tid; t < S * EV; t += R_THREADS) {  // the latest edge to pick k wins
+    if (e_flag[t] != 2) continue;
+    const int s = t / EV, k = t % EV, base = s * EV, ne = s_nv[s];
+    for (int i = k + 1; i < ne; ++i) {
+      if (e_jks[base + i] == k) e_ovs[t] = e_jvs[base + i];
+      if (e_jke[base + i] == k) e_ove[t] = e_jve[base + i];
+    }
+  }
+  __syncthreads();
+
+  // ---- phase B: spans per (sprite, canvas row); sprites in chunks that fit the lists ---
+  for (int s_begin = 0; s_begin < S;) {
+    int s_end = s_begin, rows_used = 0;
+    while (s_end < S && (s_end == s_begin || rows_used + s_rcnt[s_end] <= L.list_rows)) {
+      rows_used += s_rcnt[s_end];
+      ++s_end;
+    }
+    if (tid == 0) {
+      int off = 0;
+      for (int s = s_begin; s < s_end; ++s) { s_roff[s] = off; off += s_rcnt[s]; }
+    }
+    for (int i = tid; i < min(rows_used, L.list_rows); i += R_THREADS) s_lcnt[i] = 0;
+    __syncthreads();
+    // B1: edge-parallel crossing insertion
+    for (int t = tid + s_begin * EV; t < s_end * EV; t += R_THREADS) {
+      if (e_flag[t] != 2) continue;
+      const int s = t / EV;
+      if (s_rcnt[s] == 0) continue;
+      const int r0 = s_r0[s], r1 = r0 + s_rcnt[s] - 1, p_ymax = s_pymax[s];
+      const int ymin = e_ymin[t], ymax = e_ymax[t], y0 = e_y0[t], x0 = e_x0[t];
+      const float dx = e_dx[t], ovs = e_ovs[t], ove = e_ove[t];
+      for (int y = max(ymin, r0); y <= min(ymax, r1); ++y) {
+        float x = edge_x_at(y, y0, dx, x0);
+        if (y == ymin && !isnan(ovs)) x = ovs;
+        if (y == p_ymax && y == ymax && !isnan(ove)) x = ove;
+        const int twice = (y == ymax && y < p_ymax) ? 2 : 1;  // edge ending on an interior row
+        const int row = s_roff[s] + (y - r0);
+        if (row < L.list_rows) {
+          const int at = atomicAdd(&s_lcnt[row], twice);
+          if (at + twice <= CAP) {
+            s_list[row * CAP + at] = x;
+            if (twice == 2) s_list[row * CAP + at + 1] = x;
+          } else {
+            s_overflow = 1;
+          }
+        } else {
+          s_overflow = 1;
+        }
+      }
+    }
+    __syncthreads();
+    // B2: row-parallel sort + Pillow's pairing rule + horizontal edges
+    for (int t = tid; t < rows_used; t += R_THREADS) {
+      int s = s_begin, rem = t;
       while (rem >= s_rcnt[s]) { rem -= s_rcnt[s]; ++s; }
       const int y = s_r0[s] + rem;
+      const int row = s_roff[s] + rem;
       int lxs[MAX_ROW_SPANS], lxe[MAX_ROW_SPANS];
+      int n = 0;
       bool ovf = false;
-      const int base = s * SWB_MAX_VERTS;
-      const int n = scan_row(e_x0 + base, e_y0 + base, e_ymin + base, e_ymax + base, e_dx + base,
-                             e_flag + base, s_ne[s], y, s_pymax[s], rd.CW, lxs, lxe, ovf);
+      if (row < L.list_rows) {
+        float *xx = s_list + row * CAP;
+        const int j = min(s_lcnt[row], CAP);
+        for (int a = 1; a < j; ++a) {  // insertion sort, ascending
+          const float v = xx[a];
+          int b = a - 1;
+          while (b >= 0 && xx[b] > v) { xx[b + 1] = xx[b]; --b; }
+          xx[b + 1] = v;
+        }
+        int x_pos = 0;
+        for (int i = 1; i < j; i += 2) {
+          const int x_end = round_down_f(xx[i]);
+          if (x_end < x_pos) continue;
+          if (xx[i - 1] > (float)x_pos) {
+            x_pos = round_up_f(xx[i - 1]);
+            if (x_end < x_pos) continue;
+          }
+          const int xs = max(x_pos, 0), xe = min(x_end, rd.CW - 1);
+          if (xs <= xe) add_span(lxs, lxe, n, xs, xe, ovf);
+          x_pos = x_end + 1;
+        }
+      }
+      const int nh = s_nh[s];
+      for (int h = 0; h < nh; ++h) {
+        const short *hl = s_hl + ((size_t)s * EV + h) * 3;
+        if (hl[0] == y) add_span(lxs, lxe, n, hl[1], hl[2], ovf);
+      }
       if (n > M) ovf = true;
       uint32_t *dst = s_spans + ((size_t)s * n_rows + (y - row_b0)) * M;
       for (int k = 0; k < min(n, M); ++k) dst[k] = (uint32_t)lxs[k] | ((uint32_t)lxe[k] << 16);
       if (n > 0) atomicOr(&s_rowmask[y - row_b0], 1u << s);
       if (ovf) s_overflow = 1;
     }
+    __syncthreads();
+    s_begin = s_end;
+  }
+
+  {  // background fill of the staged frame (the scratch area is free again)
+    const uint32_t r = rd.bg & 255u, g = (rd.bg >> 8) & 255u, b = (rd.bg >> 16) & 255u;
+    const int n_bytes = n_yo * rd.W * 3;
+    if (r == g && g == b) {
+      const uint32_t w = r * 0x01010101u;
+      uint32_t *f32 = reinterpret_cast<uint32_t *>(s_frame);
+      for (int i = tid; i < (n_bytes + 3) / 4; i += R_THREADS) f32[i] = w;
+    } else {
+      for (int i = tid; i < n_yo * rd.W; i += R_THREADS) {
+        s_frame[3 * i] = (uint8_t)r; s_frame[3 * i + 1] = (uint8_t)g; s_frame[3 * i + 2] = (uint8_t)b;
+      }
+    }
   }
   __syncthreads();
 
   // ---- phase C: per sprite region, tiles of TILE_Y x TILE_X outputs ----------------
-  const uint32_t bg_r = rd.bg & 255u, bg_g = (rd.bg >> 8) & 255u, bg_b = (rd.bg >> 16) & 255u;
+  const int bg_r = rd.bg & 255u, bg_g = (rd.bg >> 8) & 255u, bg_b = (rd.bg >> 16) & 255u;
+  const uint2 bg_h = make_uint2((uint32_t)bg_r | ((uint32_t)bg_g << 16), (uint32_t)bg_b);
+  const int hw = tid >> 4, c = tid & 15;  // half-warp id (0..15), column within the tile
   for (int s = 0; s < S; ++s) {
     const int ryo0 = s_region[s * 4 + 0], ryo1 = s_region[s * 4 + 1];
     const int rxo0 = s_region[s * 4 + 2], rxo1 = s_region[s * 4 + 3];
@@ -360,70 +433,72 @@ render_kernel(DevState st, RasterDev rd, uint8_t *__restrict__ frames, int smem_
       const int nr = tr1 - tr0;
       for (int tx0 = rxo0; tx0 <= rxo1; tx0 += TILE_X) {
         const int nx = min(TILE_X, rxo1 - tx0 + 1);
-        // ---- H pass ----
-        for (int it = tid; it < nr * nx; it += R_THREADS) {
-          const int r = it / nx, c = it - r * nx;
-          const int y = tr0 + r, xo = tx0 + c;
-          const uint32_t rmask = s_rowmask[y - row_b0];
-          uint32_t orr = bg_r, og = bg_g, ob = bg_b;
-          if (rmask) {
-            const int xmin = rd.ax.win_min[xo];
-            const int len = rd.ax.win_len[xo];
-            const int32_t *P = rd.ax.prefix + (int)rd.ax.win_cls[xo] * 33;
-            const uint32_t full = (len >= 32) ? 0xFFFFFFFFu : ((1u << len) - 1u);
-            const int ktot = P[len];
-            int ar = (int)bg_r * ktot, ag = (int)bg_g * ktot, ab = (int)bg_b * ktot;
-            uint32_t covered = 0u;
-            uint32_t rem = rmask;
-            while (rem && covered != full) {
-              const int sp = 31 - __clz(rem);  // front-most remaining sprite
-              rem &= ~(1u << sp);
-              const uint32_t *spn = s_spans + ((size_t)sp * n_rows + (y - row_b0)) * M;
-              uint32_t m = 0u;
-              for (int k = 0; k < M; ++k) {
-                const uint32_t w = spn[k];
-                const int xs = (int)(w & 0xFFFFu), xe = (int)(w >> 16);
-                const int a = max(xs, xmin) - xmin, b = min(xe, xmin + len - 1) - xmin;
-                if (a <= b) m |= ((2u << b) - 1u) & ~((1u << a) - 1u);
-              }
-              uint32_t vis = m & ~covered;
-              covered |= m;
-              if (vis) {
-                const uint32_t col = (uint32_t)s_rgb[sp];
-                const int dr = (int)(col & 255u) - (int)bg_r, dg = (int)((col >> 8) & 255u) - (int)bg_g,
-                          db = (int)((col >> 16) & 255u) - (int)bg_b;
-                int wsum = 0;
-                while (vis) {
-                  const int lo = __ffs(vis) - 1;
-                  const uint32_t t = vis >> lo;
-                  const int run = (t == 0xFFFFFFFFu) ? 32 : (__ffs(~t) - 1);
-                  wsum += P[lo + run] - P[lo];
-                  vis = (lo + run >= 32) ? 0u : (vis & ~((1u << (lo + run)) - 1u));
+        const int xo = tx0 + c;
+        // ---- H pass: half-warp per canvas row, lane = output column ----
+        if (c < nx) {
+          const int xmin = rd.ax.win_min[xo];
+          const int len = rd.ax.win_len[xo];
+          const int32_t *P = s_prefix + (int)rd.ax.win_cls[xo] * 33;
+          const uint32_t full = (len >= 32) ? 0xFFFFFFFFu : ((1u << len) - 1u);
+          const int ktot = P[len];
+          const int xlast = xmin + len - 1;
+          for (int r = hw; r < nr; r += R_THREADS / 16) {
+            const int y = tr0 + r;
+            const uint32_t rmask = s_rowmask[y - row_b0];
+            uint2 hval = bg_h;
+            if (rmask) {
+              int ar = bg_r * ktot, ag = bg_g * ktot, ab = bg_b * ktot;
+              uint32_t covered = 0u;
+              uint32_t rem = rmask;
+              while (rem && covered != full) {
+                const int sp = 31 - __clz(rem);  // front-most remaining sprite
+                rem &= ~(1u << sp);
+                const uint32_t *spn = s_spans + ((size_t)sp * n_rows + (y - row_b0)) * M;
+                uint32_t m = 0u;
+                for (int k = 0; k < M; ++k) {
+                  const uint32_t w = spn[k];
+                  const int a = max((int)(w & 0xFFFFu), xmin) - xmin;
+                  const int b = min((int)(w >> 16), xlast) - xmin;
+                  if (a <= b) m |= ((2u << b) - 1u) & ~((1u << a) - 1u);
                 }
-                ar += dr * wsum; ag += dg * wsum; ab += db * wsum;
+                uint32_t vis = m & ~covered;
+                covered |= m;
+                if (vis) {
+                  const uint32_t col = (uint32_t)s_rgb[sp];
+                  int wsum = 0;
+                  do {
+                    const int lo = __ffs(vis) - 1;
+                    const uint32_t t = vis >> lo;
+                    const int run = (t == 0xFFFFFFFFu) ? 32 : (__ffs(~t) - 1);
+                    wsum += P[lo + run] - P[lo];
+                    vis = (lo + run >= 32) ? 0u : (vis & ~((1u << (lo + run)) - 1u));
+                  } while (vis);
+                  ar += ((int)(col & 255u) - bg_r) * wsum;
+                  ag += ((int)((col >> 8) & 255u) - bg_g) * wsum;
+                  ab += ((int)((col >> 16) & 255u) - bg_b) * wsum;
+                }
               }
+              hval = make_uint2(clip8_q22(ar + (1 << 21)) | (clip8_q22(ag + (1 << 21)) << 16),
+                                clip8_q22(ab + (1 << 21)));
             }
-            orr = clip8_q22(ar + (1 << 21));
-            og = clip8_q22(ag + (1 << 21));
-            ob = clip8_q22(ab + (1 << 21));
+            s_ht[r * TILE_X + c] = hval;
           }
-          s_ht[r * TILE_X + c] = make_uint2(orr | (og << 16), ob);
         }
         __syncthreads();
-        // ---- V pass ----
-        for (int it = tid; it < ny * nx; it += R_THREADS) {
-          const int ly = it / nx, c = it - ly * nx;
-          const int yo = ty0 + ly, xo = tx0 + c;
+        // ---- V pass: thread = (output row hw, column c) ----
+        if (hw < ny && c < nx) {
+          const int yo = ty0 + hw;
           const int rbase = rd.ay.win_min[yo] - tr0;
-          const int32_t *prog = rd.ay.program + (int)rd.ay.win_cls[yo] * PROG_STRIDE;
+          const int32_t *prog = s_prog + (int)rd.ay.win_cls[yo] * PROG_STRIDE;
           const int np = prog[0], ns = prog[1];
           int ar = 1 << 21, ag = 1 << 21, ab = 1 << 21;
           const int32_t *pp = prog + 2;
+          const uint2 *col_ht = s_ht + rbase * TILE_X + c;
           for (int k = 0; k < np; ++k) {
             const int ab_idx = pp[2 * k];
             const int kk = pp[2 * k + 1];
-            const uint2 u = s_ht[(rbase + (ab_idx & 255)) * TILE_X + c];
-            const uint2 v = s_ht[(rbase + (ab_idx >> 8)) * TILE_X + c];
+            const uint2 u = col_ht[(ab_idx & 255) * TILE_X];
+            const uint2 v = col_ht[(ab_idx >> 8) * TILE_X];
             const uint32_t rg = u.x + v.x, bb = u.y + v.y;
             ar += (int)(rg & 0xFFFFu) * kk;
             ag += (int)(rg >> 16) * kk;
@@ -433,7 +508,7 @@ render_kernel(DevState st, RasterDev rd, uint8_t *__restrict__ frames, int smem_
           for (int k = 0; k < ns; ++k) {
             const int a_idx = ps[2 * k];
             const int kk = ps[2 * k + 1];
-            const uint2 u = s_ht[(rbase + a_idx) * TILE_X + c];
+            const uint2 u = col_ht[a_idx * TILE_X];
             ar += (int)(u.x & 0xFFFFu) * kk;
             ag += (int)(u.x >> 16) * kk;
             ab += (int)u.y * kk;

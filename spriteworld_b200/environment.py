@@ -1,0 +1,370 @@
+"""Spriteworld environments on the B200 engine.
+
+`Environment` is the drop-in for the reference's `spriteworld/environment.py:27-161`: same
+constructor, `reset()/step()/observation_spec()/action_spec()/state()/success()`, dm_env
+TimeSteps with NumPy observations, same auto-reset cadence and the same calls to
+`init_sprites()` (hence the same draws from `np.random`) -- but every step runs on the
+GPU through the C-ABI.
+
+`BatchedEnvironment` advances `n_envs` independent copies of that environment in
+lockstep: actions, rewards, step types and frames are device tensors, scenes come from a
+device-resident pool of host-sampled scenes (`init_sprites.batch(n)`) that the step kernel
+draws from when an env auto-resets, so no host work sits between two steps except the
+periodic pool refill.
+"""
+import collections
+
+import numpy as np
+import torch
+
+from spriteworld_b200 import _dm_env as dm_env
+from spriteworld_b200 import _native, constants, scene
+from spriteworld_b200 import engine as engine_lib
+from spriteworld_b200 import sprite_generators
+from spriteworld_b200.renderers import pil_renderer
+
+
+def _split_renderers(renderers):
+  pil = collections.OrderedDict()
+  other = collections.OrderedDict()
+  for name, r in renderers.items():
+    (pil if isinstance(r, pil_renderer.PILRenderer) else other)[name] = r
+  return pil, other
+
+
+def _color_map(pil_renderers):
+  maps = {id(r.color_to_rgb): r.color_to_rgb for r in pil_renderers.values()}
+  if len(maps) > 1:
+    raise NotImplementedError('all PILRenderers of one Environment must share color_to_rgb')
+  return next(iter(maps.values())) if maps else None
+
+
+class Environment(dm_env.Environment):
+  """One Spriteworld environment (drop-in for the reference class)."""
+
+  def __init__(self, task, action_space, renderers, init_sprites, keep_in_frame=True,
+               max_episode_length=1000, metadata=None, device=0, max_sprites=None):
+    self._task = task
+    self._action_space = action_space
+    self._renderers = renderers
+    self._init_sprites = init_sprites
+    self._keep_in_frame = keep_in_frame
+    self._max_episode_length = max_episode_length
+    self._metadata = metadata
+    self._device = device
+    self._pil, self._other = _split_renderers(renderers)
+    self._color_to_rgb = _color_map(self._pil)
+    self._nodes, self._filters = task.compile()
+    task._filters_static()
+    self._engine = None
+    self._rasters = {}
+    self._max_sprites = max_sprites
+    self._sprites = self._init_sprites()            # environment.py:68
+    self._step_count = 0
+    self._reset_next_step = True
+    self._renderers_initialized = False
+    self._ring = 0
+    self._last = None          # (reward, step_type, success) of the last device step
+    self._load_scene(first=True)
+
+  # -- engine plumbing ---------------------------------------------------------------
+  def _ensure_engine(self, n_sprites):
+    """(Re)creates the one-env engine if it has too few sprite slots. Returns True if new."""
+    if self._engine is not None and n_sprites <= self._engine.n_slots:
+      return False
+    slots = max(8, n_sprites, self._max_sprites or 0)
+    if self._engine is not None:
+      for r in self._rasters.values():
+        r.close()
+      self._engine.close()
+    self._engine = engine_lib.Engine(
+        1, slots, 2, self._action_space.compile(), self._nodes, constants.SHAPES,
+        keep_in_frame=self._keep_in_frame,
+        max_episode_length=int(min(self._max_episode_length, 2 ** 31 - 1)), device=self._device)
+    self._rasters = {
+        name: engine_lib.Raster(self._engine, r.width, r.height, r.anti_aliasing, r.bg_color)
+        for name, r in self._pil.items()}
+    return True
+
+  def _load_scene(self, first=False):
+    """Uploads self._sprites: as the live scene (constructor) or as the scene the next
+    reset step switches to (ring of two slots)."""
+    fresh = self._ensure_engine(len(self._sprites))
+    eng = self._engine
+    layout = sprite_generators.layout_from_sprite_lists([self._sprites])
+    batch = scene.arrays_from_layout(layout, eng.n_slots, self._filters, self._color_to_rgb)
+    if first or fresh:
+      eng.upload_scenes(batch, [0], [0])
+      eng.upload_state(pos_x=batch['x'], pos_y=batch['y'], cursor=[0], step_count=[0],
+                       reset_next=[1])
+      self._ring = 0
+    if not first:
+      self._ring = (self._ring + 1) % 2
+      eng.upload_scenes(batch, [0], [self._ring])
+
+  def _sync_sprites(self):
+    """Copies the device positions into the host Sprite objects."""
+    state = self._engine.download_state()
+    n, S = len(self._sprites), self._engine.n_slots
+    for j, s in enumerate(self._sprites):
+      s._position[0] = state['pos_x'][0, S - n + j]
+      s._position[1] = state['pos_y'][0, S - n + j]
+
+  def _device_action(self, action):
+    kind = self._action_space.compile()['kind']
+    if kind == 'embodied':
+      if action[1] not in (0, 1, 2, 3):
+        raise KeyError(action[1])
+      a = np.array([[int(bool(action[0])), int(action[1])]], np.int32)
+    else:
+      a = np.asarray(self._action_space.apply_noise_to_action(np.asarray(action)))
+      a = a.reshape(1, 4)
+      if a.dtype != np.float32:
+        a = a.astype(np.float64)
+    return torch.from_numpy(np.ascontiguousarray(a)).to(self._engine.device)
+
+  def _run_step(self, action_tensor):
+    eng = self._engine
+    res = eng.step(action_tensor)
+    frames = {name: eng.render(r) for name, r in self._rasters.items()}
+    torch.cuda.synchronize(eng.device)
+    status = int(res.status[0].item())
+    if status & _native.ENV_CLUSTER_LABELS:
+      raise ValueError('Number of labels is invalid for the Davies-Bouldin score')
+    if status & _native.ENV_CLUSTER_ZERODIV:
+      raise ZeroDivisionError('float division by zero')
+    self._last = (float(res.reward[0].item()), int(res.step_type[0].item()),
+                  bool(res.success[0].item()))
+    self._sync_sprites()
+    return {name: f[0].cpu().numpy() for name, f in frames.items()}
+
+  def _dummy_action(self):
+    if self._action_space.compile()['kind'] == 'embodied':
+      return torch.zeros((1, 2), dtype=torch.int32, device=self._engine.device)
+    return torch.zeros((1, 4), dtype=torch.float32, device=self._engine.device)
+
+  # -- dm_env API ----------------------------------------------------------------------
+  def reset(self):
+    self._sprites = self._init_sprites()            # environment.py:75
+    self._step_count = 0
+    self._reset_next_step = False
+    self._load_scene()
+    self._engine.request_reset()
+    images = self._run_step(self._dummy_action())
+    return dm_env.restart(self._observation(images))
+
+  def success(self):
+    return self._task.success(self._sprites) if self._last is None else self._last[2]
+
+  def step(self, action):
+    if self._reset_next_step:
+      return self.reset()
+    self._step_count += 1
+    images = self._run_step(self._device_action(action))
+    reward, step_type, _ = self._last
+    observation = self._observation(images)
+    if step_type == _native.STEP_LAST:
+      self._reset_next_step = True
+      return dm_env.termination(reward=reward, observation=observation)
+    return dm_env.transition(reward=reward, observation=observation)
+
+  def sample_contained_position(self):
+    sprite = self._sprites[np.random.randint(len(self._sprites))]
+    return sprite.sample_contained_position()
+
+  def state(self):
+    global_state = {'success': self.success()}
+    if self._metadata:
+      global_state['metadata'] = self._metadata
+    return {'sprites': self._sprites, 'global_state': global_state}
+
+  def _observation(self, images):
+    state = self.state() if self._other else None
+    out = {}
+    for name in self._renderers:
+      if name in images:
+        out[name] = images[name]
+      else:
+        out[name] = self._other[name].render(**state)
+    return out
+
+  def observation(self):
+    """Observation of the current state (renders on the device)."""
+    eng = self._engine
+    frames = {name: eng.render(r) for name, r in self._rasters.items()}
+    torch.cuda.synchronize(eng.device)
+    return self._observation({name: f[0].cpu().numpy() for name, f in frames.items()})
+
+  def observation_spec(self):
+    if not self._renderers_initialized:
+      self.observation()
+      self._renderers_initialized = True
+    return {name: r.observation_spec() for name, r in self._renderers.items()}
+
+  def action_spec(self):
+    return self._action_space.action_spec()
+
+  @property
+  def action_space(self):
+    return self._action_space
+
+  def close(self):
+    if self._engine is not None:
+      for r in self._rasters.values():
+        r.close()
+      self._engine.close()
+      self._engine = None
+
+
+BatchedTimeStep = collections.namedtuple(
+    'BatchedTimeStep', ['step_type', 'reward', 'discount', 'observation', 'success', 'status'])
+
+
+class BatchedEnvironment(object):
+  """`n_envs` Spriteworld environments advanced in lockstep on one GPU.
+
+  step(actions) takes a (n_envs, 4) float32/float64 or (n_envs, 2) int32 array/tensor and
+  returns a BatchedTimeStep of device tensors: step_type int8 (dm_env.StepType values),
+  reward float64 (0 on FIRST), discount float32 (1 MID/FIRST, 0 LAST), observation dict
+  name -> uint8 (n_envs, H, W, 3), success uint8, status uint8 (per-env task errors the
+  reference would raise: _native.ENV_*).
+  """
+
+  def __init__(self, task, action_space, renderers, init_sprites, keep_in_frame=True,
+               max_episode_length=1000, metadata=None, n_envs=1, n_slots=None, pool_depth=8,
+               device=0, rng=None, env_offset=0):
+    self._task, self._action_space = task, action_space
+    self._renderers = renderers
+    self._init_sprites = init_sprites
+    self._metadata = metadata
+    self.n_envs = int(n_envs)
+    self._rng = rng if rng is not None else np.random
+    self._pil, self._other = _split_renderers(renderers)
+    unsupported = [n for n, r in self._other.items() if not hasattr(r, 'render_batch')]
+    if unsupported:
+      raise NotImplementedError('renderers %s have no batched form' % unsupported)
+    self._color_to_rgb = _color_map(self._pil)
+    self._nodes, self._filters = task.compile()
+    task._filters_static()
+    self._K = max(3, int(pool_depth))
+    E, K = self.n_envs, self._K
+    first = self._sample(E * K)
+    slots = n_slots or max(1, int(first.count.max()))
+    self._engine = engine_lib.Engine(
+        E, slots, K, action_space.compile(), self._nodes, constants.SHAPES,
+        keep_in_frame=keep_in_frame,
+        max_episode_length=int(min(max_episode_length, 2 ** 31 - 1)), device=device)
+    self._rasters = collections.OrderedDict(
+        (name, engine_lib.Raster(self._engine, r.width, r.height, r.anti_aliasing, r.bg_color))
+        for name, r in self._pil.items())
+    self._frames = {name: r.new_frames() for name, r in self._rasters.items()}
+    batch0 = self._upload(first, np.repeat(np.arange(E), K), np.tile(np.arange(K), E))
+    # env e starts on its scene 0 (the constructor's sample, environment.py:68) and is about
+    # to reset (environment.py:70)
+    self._engine.upload_state(pos_x=batch0['x'][::K], pos_y=batch0['y'][::K],
+                              cursor=np.zeros(E), step_count=np.zeros(E), reset_next=np.ones(E))
+    # ring bookkeeping in absolute scene indices (ring slot = index % K)
+    self._refilled_upto = np.full(E, K - 1, np.int64)   # newest fresh scene of each env
+    self._consumed = np.zeros(E, np.int64)              # scene each env is currently on
+    self._cursor_seen = np.zeros(E, np.int64)
+    self._steps_since_check = 0
+    # an env consumes at most one scene per two steps, so K-1 fresh scenes last 2(K-2) steps
+    self._check_every = max(1, 2 * (K - 2))
+
+  # -- scenes ----------------------------------------------------------------------------
+  def _sample(self, n):
+    return sprite_generators.batch_of(self._init_sprites, n, self._rng)
+
+  def _upload(self, layout, env_ids, ring_slots):
+    batch = scene.arrays_from_layout(layout, self._engine.n_slots, self._filters,
+                                     self._color_to_rgb)
+    self._engine.upload_scenes(batch, env_ids, ring_slots)
+    return batch
+
+  def _refill(self):
+    """Re-samples the ring slots the device has consumed since the last check."""
+    state = self._engine.download_state()
+    K = self._K
+    cur = state['cursor'].astype(np.int64)
+    advanced = (cur - self._cursor_seen) % K
+    self._consumed += advanced
+    self._cursor_seen = cur
+    # scenes with absolute index <= consumed are used up; keep K-1 fresh ones ahead
+    want_upto = self._consumed + (K - 1)
+    n_new = want_upto - self._refilled_upto
+    total = int(n_new.sum())
+    if total <= 0:
+      return
+    env_ids = np.repeat(np.arange(self.n_envs), n_new)
+    offs = np.concatenate([np.arange(1, n + 1) for n in n_new if n > 0])
+    absolute = np.repeat(self._refilled_upto, n_new) + offs
+    layout = self._sample(total)
+    self._upload(layout, env_ids, absolute % K)
+    self._refilled_upto = want_upto
+
+  # -- API ---------------------------------------------------------------------------------
+  @property
+  def engine(self):
+    return self._engine
+
+  def _to_device(self, actions):
+    dev = self._engine.device
+    if isinstance(actions, torch.Tensor):
+      t = actions
+    else:
+      a = np.asarray(actions)
+      if self._action_space.compile()['kind'] == 'embodied':
+        a = a.astype(np.int32)
+      elif a.dtype != np.float32:
+        a = a.astype(np.float64)
+      t = torch.from_numpy(np.ascontiguousarray(a))
+    return t.to(dev).contiguous()
+
+  def _timestep(self, res):
+    obs = collections.OrderedDict()
+    for name in self._renderers:
+      if name in self._frames:
+        obs[name] = self._frames[name]
+      else:
+        obs[name] = self._other[name].render_batch(self, res)
+    discount = (res.step_type != _native.STEP_LAST).to(torch.float32)
+    return BatchedTimeStep(res.step_type, res.reward, discount, obs, res.success, res.status)
+
+  def step(self, actions):
+    eng = self._engine
+    self._steps_since_check += 1
+    if self._steps_since_check >= self._check_every:
+      self._refill()
+      self._steps_since_check = 0
+    t = self._to_device(actions)
+    names = list(self._rasters)
+    if names:
+      res = eng.step(t, self._rasters[names[0]], self._frames[names[0]])
+      for name in names[1:]:
+        eng.render(self._rasters[name], self._frames[name])
+    else:
+      res = eng.step(t)
+    return self._timestep(res)
+
+  def reset(self):
+    """Restarts every env from its next pooled scene; returns the FIRST timestep."""
+    self._engine.request_reset()
+    kind = self._action_space.compile()['kind']
+    shape, dtype = ((self.n_envs, 2), torch.int32) if kind == 'embodied' else (
+        (self.n_envs, 4), torch.float32)
+    return self.step(torch.zeros(shape, dtype=dtype, device=self._engine.device))
+
+  def observation_spec(self):
+    return {name: r.observation_spec() for name, r in self._renderers.items()}
+
+  def action_spec(self):
+    return self._action_space.action_spec()
+
+  @property
+  def action_space(self):
+    return self._action_space
+
+  def close(self):
+    for r in self._rasters.values():
+      r.close()
+    self._engine.close()
