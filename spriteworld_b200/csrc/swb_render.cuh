@@ -9,16 +9,17 @@
 //                 its crossing with on its first row / on the polygon's last row.
 //   B  spans      Pillow's scan conversion.  B1 is edge-parallel: every edge drops its
 //                 float32 crossing (twice where it ends on an interior row) into the
-//                 crossing list of each canvas row it spans.  B2 is row-parallel: sort the
-//                 list, pair it up with Pillow's ROUND_UP/ROUND_DOWN rule, add horizontal
-//                 edges -> <= M merged [xs, xe] spans per (sprite, row).
+//                 crossing list of each canvas row it spans.  B2 is row-parallel: per
+//                 sprite, front to back, sort the list, pair it up with Pillow's
+//                 ROUND_UP/ROUND_DOWN rule, add horizontal edges, and fold the spans into
+//                 the row's list of VISIBLE segments (x range + sprite), i.e. the painter's
+//                 algorithm resolved once per canvas row.
 //   C  per sprite region (the outputs whose 2-D tap window can see the sprite), in tiles
-//      of 16x16 outputs:
-//        H  horizontal LANCZOS pass of the canvas rows the tile needs, one half-warp per
-//           canvas row.  A canvas row is piecewise constant, so an output is
-//           bg*K + sum_runs (colour-bg) * (P[b]-P[a]) with P the prefix sums of the
-//           22-bit tap vector; occlusion is resolved front to back with a <=32-bit
-//           coverage mask of the tap window.  clip8'ed like Pillow's uint8 intermediate.
+//      sized to a 20 KB buffer of H values:
+//        H  horizontal LANCZOS pass of the canvas rows the tile needs.  A canvas row is piecewise constant, so an output is
+//           bg*K + sum_segments (colour-bg) * (P[b]-P[a]) with P the prefix sums of the
+//           22-bit tap vector and [a, b) the segment clamped to the tap window
+//           (branch-free).  clip8'ed like Pillow's uint8 intermediate.
 //        V  vertical pass over the tile's H values (paired taps: equal coefficients share
 //           one multiply), clip8, written into the frame staged in shared memory.
 //   D  the staged frame (background + tiles) goes to HBM as 128-bit stores, rows flipped
@@ -34,16 +35,17 @@
 namespace swb {
 
 constexpr int R_THREADS = 256;
-constexpr int TILE_Y = 16;
-constexpr int TILE_X = 16;
+constexpr int TILE_Y_MAX = 32;    // output rows per tile
+constexpr int TILE_X_MAX = 32;    // output columns per tile
+constexpr int HT_ITEMS = 2560;    // H values a tile may hold (rows x columns)
 constexpr int MAX_ROW_SPANS = 12;
 constexpr int EV = SWB_MAX_VERTS;  // edge slots per sprite
 
 struct RenderLayout {
   int S, rows, M, band_rows, W, aa, ncx, ncy, cap;
   int off_pos, off_meta, off_iv, off_edge_i, off_edge_f, off_edge_b, off_hl, off_region;
-  int off_rowmask, off_spans, off_prefix, off_prog, off_scratch, off_frame, total;
-  int ht_rows, scratch_bytes, list_rows;
+  int off_nseg, off_segs, off_prefix, off_prog, off_xwin, off_ywin, off_scratch, off_frame, total;
+  int scratch_bytes, list_rows, segcap;
   __host__ __device__ RenderLayout(int S_, int rows_, int M_, int band_rows_, int W_, int aa_,
                                    int ncx_, int ncy_)
       : S(S_), rows(rows_), M(M_), band_rows(band_rows_), W(W_), aa(aa_), ncx(ncx_), ncy(ncy_) {
@@ -57,13 +59,15 @@ struct RenderLayout {
     off_edge_b = take(S * EV * 3);         // flag, join partner (start), join partner (end)
     off_hl = take(S * EV * 3 * 2);         // horizontal edges: y, xmin, xmax (int16)
     off_region = take(S * 4 * 2);
-    off_rowmask = take(rows * 4);
-    off_spans = take(S * rows * M * 4);
+    segcap = (M > 1 || S > 8) ? 16 : 8;    // visible segments kept per canvas row
+    off_nseg = take(rows);
+    off_segs = take(rows * segcap * 4);
     off_prefix = take(ncx * 33 * 4);
     off_prog = take(ncy * PROG_STRIDE * 4);
-    ht_rows = TILE_Y * aa + 32;
+    off_xwin = take(W * 4);                // per output column: win_min | len<<16 | cls<<24
+    off_ywin = take(band_rows * 4);
     // scratch: H tile + staged frame; phase B aliases it with the per-row crossing lists
-    off_scratch = take(ht_rows * TILE_X * 8);
+    off_scratch = take(HT_ITEMS * 8);
     off_frame = take(band_rows * W * 3);
     total = o;
     scratch_bytes = total - off_scratch;
@@ -117,7 +121,6 @@ render_kernel(DevState st, RasterDev rd, uint8_t *__restrict__ frames, int smem_
   const int tid = threadIdx.x;
   const int S = st.S;
   const RenderLayout L(S, smem_rows, rd.max_spans, rd.band_rows, rd.W, rd.aa, rd.ncls_x, rd.ncls_y);
-  const int M = rd.max_spans;
 
   double *s_px = reinterpret_cast<double *>(smem + L.off_pos);
   double *s_py = s_px + S;
@@ -139,10 +142,13 @@ render_kernel(DevState st, RasterDev rd, uint8_t *__restrict__ frames, int smem_
   int8_t *e_jke = e_jks + S * EV;
   short *s_hl = reinterpret_cast<short *>(smem + L.off_hl);  // [S][EV][3]
   short *s_region = reinterpret_cast<short *>(smem + L.off_region);  // [S][4] yo0,yo1,xo0,xo1
-  uint32_t *s_rowmask = reinterpret_cast<uint32_t *>(smem + L.off_rowmask);
-  uint32_t *s_spans = reinterpret_cast<uint32_t *>(smem + L.off_spans);
+  uint8_t *s_nseg = smem + L.off_nseg;
+  uint32_t *s_segs = reinterpret_cast<uint32_t *>(smem + L.off_segs);  // xs | xe<<12 | sprite<<24
+  const int SEGCAP = L.segcap;
   int32_t *s_prefix = reinterpret_cast<int32_t *>(smem + L.off_prefix);
   int32_t *s_prog = reinterpret_cast<int32_t *>(smem + L.off_prog);
+  uint32_t *s_xwin = reinterpret_cast<uint32_t *>(smem + L.off_xwin);
+  uint32_t *s_ywin = reinterpret_cast<uint32_t *>(smem + L.off_ywin);
   uint2 *s_ht = reinterpret_cast<uint2 *>(smem + L.off_scratch);
   uint8_t *s_frame = smem + L.off_frame;
   // phase-B view of the scratch area: per-row crossing lists
@@ -177,8 +183,13 @@ render_kernel(DevState st, RasterDev rd, uint8_t *__restrict__ frames, int smem_
   }
   for (int i = tid; i < rd.ncls_x * 33; i += R_THREADS) s_prefix[i] = rd.ax.prefix[i];
   for (int i = tid; i < rd.ncls_y * PROG_STRIDE; i += R_THREADS) s_prog[i] = rd.ay.program[i];
-  for (int i = tid; i < n_rows; i += R_THREADS) s_rowmask[i] = 0u;
-  for (int i = tid; i < S * n_rows * M; i += R_THREADS) s_spans[i] = 0x0000FFFFu;  // xs > xe
+  for (int i = tid; i < n_rows; i += R_THREADS) s_nseg[i] = 0;
+  for (int i = tid; i < rd.W; i += R_THREADS)
+    s_xwin[i] = (uint32_t)(uint16_t)rd.ax.win_min[i] | ((uint32_t)rd.ax.win_len[i] << 16) |
+                ((uint32_t)rd.ax.win_cls[i] << 24);
+  for (int i = tid; i < n_yo; i += R_THREADS)
+    s_ywin[i] = (uint32_t)(uint16_t)rd.ay.win_min[yo_b0 + i] | ((uint32_t)rd.ay.win_len[yo_b0 + i] << 16) |
+                ((uint32_t)rd.ay.win_cls[yo_b0 + i] << 24);
   __syncthreads();
 
   // ---- phase A1: integer canvas vertices ----------------------------------------
@@ -316,21 +327,22 @@ render_kernel(DevState st, RasterDev rd, uint8_t *__restrict__ frames, int smem_
   }
   __syncthreads();
 
-  // ---- phase B: spans per (sprite, canvas row); sprites in chunks that fit the lists ---
-  for (int s_begin = 0; s_begin < S;) {
-    int s_end = s_begin, rows_used = 0;
-    while (s_end < S && (s_end == s_begin || rows_used + s_rcnt[s_end] <= L.list_rows)) {
-      rows_used += s_rcnt[s_end];
-      ++s_end;
+  // ---- phase B: visible segments per canvas row -----------------------------------------
+  // Sprites are taken front to back, in chunks whose crossing lists fit the scratch area.
+  for (int s_hi = S; s_hi > 0;) {
+    int s_lo = s_hi, rows_used = 0;
+    while (s_lo > 0 && (s_lo == s_hi || rows_used + s_rcnt[s_lo - 1] <= L.list_rows)) {
+      rows_used += s_rcnt[s_lo - 1];
+      --s_lo;
     }
     if (tid == 0) {
       int off = 0;
-      for (int s = s_begin; s < s_end; ++s) { s_roff[s] = off; off += s_rcnt[s]; }
+      for (int s = s_lo; s < s_hi; ++s) { s_roff[s] = off; off += s_rcnt[s]; }
     }
     for (int i = tid; i < min(rows_used, L.list_rows); i += R_THREADS) s_lcnt[i] = 0;
     __syncthreads();
     // B1: edge-parallel crossing insertion
-    for (int t = tid + s_begin * EV; t < s_end * EV; t += R_THREADS) {
+    for (int t = tid + s_lo * EV; t < s_hi * EV; t += R_THREADS) {
       if (e_flag[t] != 2) continue;
       const int s = t / EV;
       if (s_rcnt[s] == 0) continue;
@@ -357,50 +369,80 @@ render_kernel(DevState st, RasterDev rd, uint8_t *__restrict__ frames, int smem_
       }
     }
     __syncthreads();
-    // B2: row-parallel sort + Pillow's pairing rule + horizontal edges
-    for (int t = tid; t < rows_used; t += R_THREADS) {
-      int s = s_begin, rem = t;
-      while (rem >= s_rcnt[s]) { rem -= s_rcnt[s]; ++s; }
-      const int y = s_r0[s] + rem;
-      const int row = s_roff[s] + rem;
-      int lxs[MAX_ROW_SPANS], lxe[MAX_ROW_SPANS];
-      int n = 0;
+    // B2: row-parallel.  For every sprite of the chunk that touches the row, front to back:
+    // sort its crossings, apply Pillow's pairing rule, add horizontal edges, then keep the
+    // parts of its spans that no nearer sprite covers.
+    for (int ry = tid; ry < n_rows; ry += R_THREADS) {
+      const int y = row_b0 + ry;
+      uint32_t *seg = s_segs + (size_t)ry * SEGCAP;
+      int nseg = s_nseg[ry];
       bool ovf = false;
-      if (row < L.list_rows) {
-        float *xx = s_list + row * CAP;
-        const int j = min(s_lcnt[row], CAP);
-        for (int a = 1; a < j; ++a) {  // insertion sort, ascending
-          const float v = xx[a];
-          int b = a - 1;
-          while (b >= 0 && xx[b] > v) { xx[b + 1] = xx[b]; --b; }
-          xx[b + 1] = v;
-        }
-        int x_pos = 0;
-        for (int i = 1; i < j; i += 2) {
-          const int x_end = round_down_f(xx[i]);
-          if (x_end < x_pos) continue;
-          if (xx[i - 1] > (float)x_pos) {
-            x_pos = round_up_f(xx[i - 1]);
-            if (x_end < x_pos) continue;
+      for (int s = s_hi - 1; s >= s_lo; --s) {
+        const int rem = y - s_r0[s];
+        if (rem < 0 || rem >= s_rcnt[s]) continue;
+        const int row = s_roff[s] + rem;
+        int lxs[MAX_ROW_SPANS], lxe[MAX_ROW_SPANS];
+        int n = 0;
+        if (row < L.list_rows) {
+          float *xx = s_list + row * CAP;
+          const int j = min(s_lcnt[row], CAP);
+          for (int a = 1; a < j; ++a) {  // insertion sort, ascending
+            const float v = xx[a];
+            int b = a - 1;
+            while (b >= 0 && xx[b] > v) { xx[b + 1] = xx[b]; --b; }
+            xx[b + 1] = v;
           }
-          const int xs = max(x_pos, 0), xe = min(x_end, rd.CW - 1);
-          if (xs <= xe) add_span(lxs, lxe, n, xs, xe, ovf);
-          x_pos = x_end + 1;
+          int x_pos = 0;
+          for (int i = 1; i < j; i += 2) {
+            const int x_end = round_down_f(xx[i]);
+            if (x_end < x_pos) continue;
+            if (xx[i - 1] > (float)x_pos) {
+              x_pos = round_up_f(xx[i - 1]);
+              if (x_end < x_pos) continue;
+            }
+            const int xs = max(x_pos, 0), xe = min(x_end, rd.CW - 1);
+            if (xs <= xe) add_span(lxs, lxe, n, xs, xe, ovf);
+            x_pos = x_end + 1;
+          }
+        }
+        const int nh = s_nh[s];
+        for (int h = 0; h < nh; ++h) {
+          const short *hl = s_hl + ((size_t)s * EV + h) * 3;
+          if (hl[0] == y) add_span(lxs, lxe, n, hl[1], hl[2], ovf);
+        }
+        // fold: the sprite's spans minus what is already covered, kept sorted by x
+        for (int k = 0; k < n; ++k) {
+          const int b = lxe[k];
+          int cursor = lxs[k];
+          for (int i = 0; i <= nseg && cursor <= b; ++i) {
+            // gap before segment i (or after the last one)
+            int gap_end = b;
+            int next_cursor = b + 1;
+            if (i < nseg) {
+              const int xs = (int)(seg[i] & 0xFFFu), xe = (int)((seg[i] >> 12) & 0xFFFu);
+              if (xe < cursor) continue;
+              gap_end = min(b, xs - 1);
+              next_cursor = xe + 1;
+            }
+            if (cursor <= gap_end) {
+              if (nseg < SEGCAP) {
+                for (int m = nseg; m > i; --m) seg[m] = seg[m - 1];
+                seg[i] = (uint32_t)cursor | ((uint32_t)gap_end << 12) | ((uint32_t)s << 24);
+                ++nseg;
+                ++i;  // the segment we compared against moved one slot up
+              } else {
+                ovf = true;
+              }
+            }
+            cursor = max(cursor, next_cursor);
+          }
         }
       }
-      const int nh = s_nh[s];
-      for (int h = 0; h < nh; ++h) {
-        const short *hl = s_hl + ((size_t)s * EV + h) * 3;
-        if (hl[0] == y) add_span(lxs, lxe, n, hl[1], hl[2], ovf);
-      }
-      if (n > M) ovf = true;
-      uint32_t *dst = s_spans + ((size_t)s * n_rows + (y - row_b0)) * M;
-      for (int k = 0; k < min(n, M); ++k) dst[k] = (uint32_t)lxs[k] | ((uint32_t)lxe[k] << 16);
-      if (n > 0) atomicOr(&s_rowmask[y - row_b0], 1u << s);
+      s_nseg[ry] = (uint8_t)nseg;
       if (ovf) s_overflow = 1;
     }
     __syncthreads();
-    s_begin = s_end;
+    s_hi = s_lo;
   }
 
   {  // background fill of the staged frame (the scratch area is free again)
@@ -418,102 +460,92 @@ render_kernel(DevState st, RasterDev rd, uint8_t *__restrict__ frames, int smem_
   }
   __syncthreads();
 
-  // ---- phase C: per sprite region, tiles of TILE_Y x TILE_X outputs ----------------
+  // ---- phase C: per sprite region, in tiles sized to the H buffer -----------------------
+  // A region of h x w outputs is cut into ceil(h/32) row blocks and, per row block, into as
+  // few equal column blocks as fit HT_ITEMS H values (columns need no halo, rows do).
   const int bg_r = rd.bg & 255u, bg_g = (rd.bg >> 8) & 255u, bg_b = (rd.bg >> 16) & 255u;
   const uint2 bg_h = make_uint2((uint32_t)bg_r | ((uint32_t)bg_g << 16), (uint32_t)bg_b);
-  const int hw = tid >> 4, c = tid & 15;  // half-warp id (0..15), column within the tile
   for (int s = 0; s < S; ++s) {
     const int ryo0 = s_region[s * 4 + 0], ryo1 = s_region[s * 4 + 1];
     const int rxo0 = s_region[s * 4 + 2], rxo1 = s_region[s * 4 + 3];
     if (ryo1 < ryo0 || rxo1 < rxo0) continue;
-    for (int ty0 = ryo0; ty0 <= ryo1; ty0 += TILE_Y) {
-      const int ny = min(TILE_Y, ryo1 - ty0 + 1);
-      const int tr0 = rd.ay.win_min[ty0];
-      const int tr1 = rd.ay.win_min[ty0 + ny - 1] + rd.ay.win_len[ty0 + ny - 1];  // exclusive
+    const int rh = ryo1 - ryo0 + 1, rw = rxo1 - rxo0 + 1;
+    const int nty = (rh + TILE_Y_MAX - 1) / TILE_Y_MAX;
+    const int ny_blk = (rh + nty - 1) / nty;
+    for (int ty0 = ryo0; ty0 <= ryo1; ty0 += ny_blk) {
+      const int ny = min(ny_blk, ryo1 - ty0 + 1);
+      const uint32_t yw0 = s_ywin[ty0 - yo_b0], yw1 = s_ywin[ty0 + ny - 1 - yo_b0];
+      const int tr0 = (int)(int16_t)(yw0 & 0xFFFFu);
+      const int tr1 = (int)(int16_t)(yw1 & 0xFFFFu) + (int)((yw1 >> 16) & 0xFFu);  // exclusive
       const int nr = tr1 - tr0;
-      for (int tx0 = rxo0; tx0 <= rxo1; tx0 += TILE_X) {
-        const int nx = min(TILE_X, rxo1 - tx0 + 1);
-        const int xo = tx0 + c;
-        // ---- H pass: half-warp per canvas row, lane = output column ----
-        if (c < nx) {
-          const int xmin = rd.ax.win_min[xo];
-          const int len = rd.ax.win_len[xo];
-          const int32_t *P = s_prefix + (int)rd.ax.win_cls[xo] * 33;
-          const uint32_t full = (len >= 32) ? 0xFFFFFFFFu : ((1u << len) - 1u);
-          const int ktot = P[len];
-          const int xlast = xmin + len - 1;
-          for (int r = hw; r < nr; r += R_THREADS / 16) {
-            const int y = tr0 + r;
-            const uint32_t rmask = s_rowmask[y - row_b0];
-            uint2 hval = bg_h;
-            if (rmask) {
-              int ar = bg_r * ktot, ag = bg_g * ktot, ab = bg_b * ktot;
-              uint32_t covered = 0u;
-              uint32_t rem = rmask;
-              while (rem && covered != full) {
-                const int sp = 31 - __clz(rem);  // front-most remaining sprite
-                rem &= ~(1u << sp);
-                const uint32_t *spn = s_spans + ((size_t)sp * n_rows + (y - row_b0)) * M;
-                uint32_t m = 0u;
-                for (int k = 0; k < M; ++k) {
-                  const uint32_t w = spn[k];
-                  const int a = max((int)(w & 0xFFFFu), xmin) - xmin;
-                  const int b = min((int)(w >> 16), xlast) - xmin;
-                  if (a <= b) m |= ((2u << b) - 1u) & ~((1u << a) - 1u);
-                }
-                uint32_t vis = m & ~covered;
-                covered |= m;
-                if (vis) {
-                  const uint32_t col = (uint32_t)s_rgb[sp];
-                  int wsum = 0;
-                  do {
-                    const int lo = __ffs(vis) - 1;
-                    const uint32_t t = vis >> lo;
-                    const int run = (t == 0xFFFFFFFFu) ? 32 : (__ffs(~t) - 1);
-                    wsum += P[lo + run] - P[lo];
-                    vis = (lo + run >= 32) ? 0u : (vis & ~((1u << (lo + run)) - 1u));
-                  } while (vis);
-                  ar += ((int)(col & 255u) - bg_r) * wsum;
-                  ag += ((int)((col >> 8) & 255u) - bg_g) * wsum;
-                  ab += ((int)((col >> 16) & 255u) - bg_b) * wsum;
-                }
-              }
-              hval = make_uint2(clip8_q22(ar + (1 << 21)) | (clip8_q22(ag + (1 << 21)) << 16),
-                                clip8_q22(ab + (1 << 21)));
+      const int nx_cap = max(1, min(TILE_X_MAX, HT_ITEMS / nr));
+      const int ntx = (rw + nx_cap - 1) / nx_cap;
+      const int nx_blk = (rw + ntx - 1) / ntx;
+      for (int tx0 = rxo0; tx0 <= rxo1; tx0 += nx_blk) {
+        const int nx = min(nx_blk, rxo1 - tx0 + 1);
+        const uint32_t inv_nx = (1u << 20) / (uint32_t)nx + 1u;  // exact for it < 2^20 / nx
+        // ---- H pass: item = (canvas row r, column c), rows of one warp are adjacent ----
+        for (int it = tid; it < nr * nx; it += R_THREADS) {
+          const int r = (int)(((uint32_t)it * inv_nx) >> 20);
+          const int c = it - r * nx;
+          const int ry = tr0 + r - row_b0;
+          const int nseg = s_nseg[ry];
+          uint2 hval = bg_h;
+          if (nseg) {
+            const uint32_t xw = s_xwin[tx0 + c];
+            const int xmin = (int)(int16_t)(xw & 0xFFFFu), len = (int)((xw >> 16) & 0xFFu);
+            const int32_t *P = s_prefix + (int)(xw >> 24) * 33;
+            const int ktot = P[len];
+            const uint32_t *seg = s_segs + (size_t)ry * SEGCAP;
+            int ar = bg_r * ktot, ag = bg_g * ktot, ab = bg_b * ktot;
+            for (int j = 0; j < nseg; ++j) {
+              const uint32_t w = seg[j];
+              const int a = min(max((int)(w & 0xFFFu) - xmin, 0), len);
+              const int b = min(max((int)((w >> 12) & 0xFFFu) + 1 - xmin, 0), len);
+              const int wt = P[b] - P[a];
+              const uint32_t col = (uint32_t)s_rgb[w >> 24];
+              ar += ((int)(col & 255u) - bg_r) * wt;
+              ag += ((int)((col >> 8) & 255u) - bg_g) * wt;
+              ab += ((int)((col >> 16) & 255u) - bg_b) * wt;
             }
-            s_ht[r * TILE_X + c] = hval;
+            hval = make_uint2(clip8_q22(ar + (1 << 21)) | (clip8_q22(ag + (1 << 21)) << 16),
+                              clip8_q22(ab + (1 << 21)));
           }
+          s_ht[it] = hval;
         }
         __syncthreads();
-        // ---- V pass: thread = (output row hw, column c) ----
-        if (hw < ny && c < nx) {
-          const int yo = ty0 + hw;
-          const int rbase = rd.ay.win_min[yo] - tr0;
-          const int32_t *prog = s_prog + (int)rd.ay.win_cls[yo] * PROG_STRIDE;
+        // ---- V pass: item = (output row ly, column c) ----
+        for (int it = tid; it < ny * nx; it += R_THREADS) {
+          const int ly = (int)(((uint32_t)it * inv_nx) >> 20);
+          const int c = it - ly * nx;
+          const int yo = ty0 + ly;
+          const uint32_t yw = s_ywin[yo - yo_b0];
+          const int rbase = (int)(int16_t)(yw & 0xFFFFu) - tr0;
+          const int32_t *prog = s_prog + (int)(yw >> 24) * PROG_STRIDE;
           const int np = prog[0], ns = prog[1];
           int ar = 1 << 21, ag = 1 << 21, ab = 1 << 21;
-          const int32_t *pp = prog + 2;
-          const uint2 *col_ht = s_ht + rbase * TILE_X + c;
+          const int2 *pp = reinterpret_cast<const int2 *>(prog + 2);
+          const uint2 *col_ht = s_ht + rbase * nx + c;
+#pragma unroll 4
           for (int k = 0; k < np; ++k) {
-            const int ab_idx = pp[2 * k];
-            const int kk = pp[2 * k + 1];
-            const uint2 u = col_ht[(ab_idx & 255) * TILE_X];
-            const uint2 v = col_ht[(ab_idx >> 8) * TILE_X];
+            const int2 pk = pp[k];  // (row a | row b << 8, coefficient)
+            const uint2 u = col_ht[(pk.x & 255) * nx];
+            const uint2 v = col_ht[(pk.x >> 8) * nx];
             const uint32_t rg = u.x + v.x, bb = u.y + v.y;
-            ar += (int)(rg & 0xFFFFu) * kk;
-            ag += (int)(rg >> 16) * kk;
-            ab += (int)bb * kk;
+            ar += (int)(rg & 0xFFFFu) * pk.y;
+            ag += (int)(rg >> 16) * pk.y;
+            ab += (int)bb * pk.y;
           }
-          const int32_t *ps = prog + 2 + 2 * 16;
+          const int2 *ps = reinterpret_cast<const int2 *>(prog + 2 + 2 * 16);
+#pragma unroll 2
           for (int k = 0; k < ns; ++k) {
-            const int a_idx = ps[2 * k];
-            const int kk = ps[2 * k + 1];
-            const uint2 u = col_ht[a_idx * TILE_X];
-            ar += (int)(u.x & 0xFFFFu) * kk;
-            ag += (int)(u.x >> 16) * kk;
-            ab += (int)u.y * kk;
+            const int2 pk = ps[k];
+            const uint2 u = col_ht[pk.x * nx];
+            ar += (int)(u.x & 0xFFFFu) * pk.y;
+            ag += (int)(u.x >> 16) * pk.y;
+            ab += (int)u.y * pk.y;
           }
-          uint8_t *px = s_frame + ((size_t)(yo - yo_b0) * rd.W + xo) * 3;
+          uint8_t *px = s_frame + ((size_t)(yo - yo_b0) * rd.W + tx0 + c) * 3;
           px[0] = (uint8_t)clip8_q22(ar);
           px[1] = (uint8_t)clip8_q22(ag);
           px[2] = (uint8_t)clip8_q22(ab);

@@ -386,7 +386,59 @@ def moving_sprites_config():
       keep_in_frame=False, max_episode_length=12)
 
 
+CONFIG_MODES = [
+    ('cobra', 'goal_finding_more_targets', ('train', 'test')),
+    ('cobra', 'goal_finding_more_distractors', ('train', 'test')),
+    ('cobra', 'goal_finding_new_position', ('train', 'test')),
+    ('cobra', 'goal_finding_new_shape', ('train', 'test')),
+    ('cobra', 'clustering', ('train', 'test')),
+    ('cobra', 'sorting', ('train', 'test')),
+    ('cobra', 'exploration', (None,)),
+    ('examples', 'goal_finding_embodied', (None,)),
+    ('examples', 'goal_finding_clustering', ('train', 'test')),
+]
+TYPE_CODES = {float: 0, np.float64: 1, np.float32: 2, int: 3, np.int32: 4, np.uint8: 5,
+              np.int64: 6, str: 7}
+
+
+def sampling_cases(seed=5, n_scenes=12):
+  """What init_sprites() of every shipped config draws from np.random.seed(seed): pins the
+  RNG call order of factor_distributions / sprite_generators."""
+  import contextlib
+  import importlib
+  import io
+  blob = {}
+  for pkg, name, modes in CONFIG_MODES:
+    mod = importlib.import_module('spriteworld.configs.%s.%s' % (pkg, name))
+    for mode in modes:
+      with contextlib.redirect_stdout(io.StringIO()):
+        cfg = mod.get_config(mode) if mode else mod.get_config()
+      np.random.seed(seed)
+      counts, values, types, shapes = [], [], [], []
+      for _ in range(n_scenes):
+        sprites = cfg['init_sprites']()
+        counts.append(len(sprites))
+        for s in sprites:
+          f = s.factors
+          shapes.append(SHAPE_IDS[f['shape']])
+          values.append([float(v) for k, v in f.items() if k != 'shape'])
+          types.append([TYPE_CODES[type(v)] for k, v in f.items() if k != 'shape'])
+      key = '%s.%s.%s' % (pkg, name, mode)
+      blob[key + '.count'] = np.array(counts, np.int32)
+      blob[key + '.values'] = np.array(values, np.float64).reshape(-1, 9)
+      blob[key + '.types'] = np.array(types, np.uint8).reshape(-1, 9)
+      blob[key + '.shapes'] = np.array(shapes, np.uint8)
+      blob[key + '.max_episode_length'] = np.array(cfg['max_episode_length'])
+      blob[key + '.task'] = np.array(json.dumps(
+          task_nodes(cfg['task'], collect_filters(cfg['task']))))
+      blob[key + '.action'] = np.array(json.dumps(action_desc(cfg['action_space'])))
+  blob['seed'] = np.array(seed)
+  np.savez_compressed(os.path.join(OUT, 'sampling.npz'), **blob)
+  print('sampling.npz: %d config/mode pairs' % (len(blob) // 7))
+
+
 def main():
+  sampling_cases()
   render_cases()
   run_episodes('goal_finding', bench_like_goal_finding, n_envs=12, n_steps=60, n_slots=5,
                action_dtype='float32', frame_envs=(0, 1, 2))
