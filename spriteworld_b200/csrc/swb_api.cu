@@ -408,8 +408,8 @@ static int launch_render(swb_engine *eng, swb_raster *r, uint8_t *frames, uint8_
   rd.max_spans = eng->max_spans;
   const RenderLayout L(eng->st.S, r->smem_rows, rd.max_spans, rd.band_rows, rd.W, rd.aa, rd.ncls_x,
                        rd.ncls_y);
-  if (L.list_rows < r->smem_rows)
-    return fail("render scratch holds %d crossing lists but a sprite may span %d canvas rows", L.list_rows,
+  if ((L.cap + rd.max_spans) * 4 * r->smem_rows > L.scratch_bytes)
+    return fail("render scratch (%d B) cannot hold one sprite spanning %d canvas rows", L.scratch_bytes,
                 r->smem_rows);
   int max_smem = 0;
   CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, eng->device));

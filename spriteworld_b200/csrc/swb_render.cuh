@@ -43,7 +43,7 @@ constexpr int EV = SWB_MAX_VERTS;  // edge slots per sprite
 
 struct RenderLayout {
   int S, rows, M, band_rows, W, aa, ncx, ncy, cap;
-  int off_pos, off_meta, off_iv, off_edge_i, off_edge_f, off_edge_b, off_hl, off_region;
+  int off_pos, off_meta, off_iv, off_edge_i, off_edge_f, off_edge_b, off_edge_yr, off_hl, off_region;
   int off_nseg, off_segs, off_prefix, off_prog, off_xwin, off_ywin, off_scratch, off_frame, total;
   int scratch_bytes, list_rows, segcap;
   __host__ __device__ RenderLayout(int S_, int rows_, int M_, int band_rows_, int W_, int aa_,
@@ -52,11 +52,12 @@ struct RenderLayout {
     int o = 0;
     auto take = [&](int bytes) { int r = o; o += (bytes + 15) & ~15; return r; };
     off_pos = take(S * 6 * 8);
-    off_meta = take(S * 14 * 4);
+    off_meta = take(S * 20 * 4);
     off_iv = take(S * EV * 2 * 4);
     off_edge_i = take(S * EV * 4 * 4);     // x0, y0, ymin, ymax
     off_edge_f = take(S * EV * 5 * 4);     // dx, ovs, ove, join nv (start), join nv (end)
     off_edge_b = take(S * EV * 3);         // flag, join partner (start), join partner (end)
+    off_edge_yr = take(S * EV * 4);        // ymin | ymax<<16 of non-horizontal edges, empty otherwise
     off_hl = take(S * EV * 3 * 2);         // horizontal edges: y, xmin, xmax (int16)
     off_region = take(S * 4 * 2);
     segcap = (M > 1 || S > 8) ? 16 : 8;    // visible segments kept per canvas row
@@ -72,7 +73,7 @@ struct RenderLayout {
     total = o;
     scratch_bytes = total - off_scratch;
     cap = (M > 1) ? 16 : 8;                // crossings kept per (sprite, row)
-    list_rows = scratch_bytes / (cap * 4 + 4);
+    list_rows = scratch_bytes / (cap * 4 + 4);  // upper bound; phase B sizes its chunks itself
   }
 };
 
@@ -130,6 +131,8 @@ render_kernel(DevState st, RasterDev rd, uint8_t *__restrict__ frames, int smem_
   int *s_xmin = s_rgb + S, *s_xmax = s_xmin + S, *s_gymin = s_xmax + S, *s_gymax = s_gymin + S;
   int *s_pymin = s_gymax + S, *s_pymax = s_pymin + S, *s_shape = s_pymax + S;
   int *s_r0 = s_shape + S, *s_rcnt = s_r0 + S, *s_nh = s_rcnt + S, *s_roff = s_nh + S;
+  int *s_dr = s_roff + S, *s_dg = s_dr + S, *s_db = s_dg + S;       // colour - background
+  int *s_pny = s_db + S, *s_pnx = s_pny + S, *s_pinv = s_pnx + S;  // tile plan of the region
   int *s_ivx = reinterpret_cast<int *>(smem + L.off_iv);
   int *s_ivy = s_ivx + S * EV;
   int *e_x0 = reinterpret_cast<int *>(smem + L.off_edge_i);
@@ -140,11 +143,13 @@ render_kernel(DevState st, RasterDev rd, uint8_t *__restrict__ frames, int smem_
   uint8_t *e_flag = smem + L.off_edge_b;
   int8_t *e_jks = reinterpret_cast<int8_t *>(e_flag + S * EV);
   int8_t *e_jke = e_jks + S * EV;
+  uint32_t *e_yr = reinterpret_cast<uint32_t *>(smem + L.off_edge_yr);
   short *s_hl = reinterpret_cast<short *>(smem + L.off_hl);  // [S][EV][3]
   short *s_region = reinterpret_cast<short *>(smem + L.off_region);  // [S][4] yo0,yo1,xo0,xo1
   uint8_t *s_nseg = smem + L.off_nseg;
   uint32_t *s_segs = reinterpret_cast<uint32_t *>(smem + L.off_segs);  // xs | xe<<12 | sprite<<24
   const int SEGCAP = L.segcap;
+  const int M = rd.max_spans;
   int32_t *s_prefix = reinterpret_cast<int32_t *>(smem + L.off_prefix);
   int32_t *s_prog = reinterpret_cast<int32_t *>(smem + L.off_prog);
   uint32_t *s_xwin = reinterpret_cast<uint32_t *>(smem + L.off_xwin);
@@ -153,8 +158,6 @@ render_kernel(DevState st, RasterDev rd, uint8_t *__restrict__ frames, int smem_
   uint8_t *s_frame = smem + L.off_frame;
   // phase-B view of the scratch area: per-row crossing lists
   const int CAP = L.cap;
-  int *s_lcnt = reinterpret_cast<int *>(smem + L.off_scratch);
-  float *s_list = reinterpret_cast<float *>(smem + L.off_scratch) + L.list_rows;
   __shared__ int s_overflow;
 
   const int yo_b0 = band * rd.band_rows;
@@ -172,7 +175,11 @@ render_kernel(DevState st, RasterDev rd, uint8_t *__restrict__ frames, int smem_
     const int shape = st.p_shape[scene];
     s_shape[tid] = shape;
     s_nv[tid] = shape ? st.shape_n[shape] : 0;
-    s_rgb[tid] = (int)st.p_rgb[scene];
+    const uint32_t col = st.p_rgb[scene];
+    s_rgb[tid] = (int)col;
+    s_dr[tid] = (int)(col & 255u) - (int)(rd.bg & 255u);
+    s_dg[tid] = (int)((col >> 8) & 255u) - (int)((rd.bg >> 8) & 255u);
+    s_db[tid] = (int)((col >> 16) & 255u) - (int)((rd.bg >> 16) & 255u);
     s_px[tid] = st.pos_x[e * S + tid];
     s_py[tid] = st.pos_y[e * S + tid];
     s_m[0 * S + tid] = st.p_m00[scene];
@@ -242,6 +249,10 @@ render_kernel(DevState st, RasterDev rd, uint8_t *__restrict__ frames, int smem_
       }
     }
     e_flag[t] = (uint8_t)flag;
+    // rows the edge crosses, clamped to int16 (canvas rows are < 4096); empty if not scanned
+    e_yr[t] = flag == 2 ? ((uint32_t)(uint16_t)(short)max(e_ymin[t], -32768) |
+                           ((uint32_t)(uint16_t)(short)min(e_ymax[t], 32767) << 16))
+                        : 0x80007FFFu;
     e_ovs[t] = nanf("");
     e_ove[t] = nanf("");
     e_jks[t] = -1;
@@ -276,6 +287,19 @@ render_kernel(DevState st, RasterDev rd, uint8_t *__restrict__ frames, int smem_
     }
     s_region[tid * 4 + 0] = yo0; s_region[tid * 4 + 1] = yo1;
     s_region[tid * 4 + 2] = xo0; s_region[tid * 4 + 3] = xo1;
+    // tile plan: ceil(h/32) row blocks; as few equal column blocks as fit HT_ITEMS H values
+    // (columns need no halo, rows do: <= ny*aa + 32 canvas rows per block)
+    int pny = 1, pnx = 1;
+    if (yo1 >= yo0 && xo1 >= xo0) {
+      const int rh = yo1 - yo0 + 1, rw = xo1 - xo0 + 1;
+      const int nty = (rh + TILE_Y_MAX - 1) / TILE_Y_MAX;
+      pny = (rh + nty - 1) / nty;
+      const int nx_cap = max(1, min(TILE_X_MAX, HT_ITEMS / (pny * rd.aa + 32)));
+      const int ntx = (rw + nx_cap - 1) / nx_cap;
+      pnx = (rw + ntx - 1) / ntx;
+    }
+    s_pny[tid] = pny; s_pnx[tid] = pnx;
+    s_pinv[tid] = (int)((1u << 20) / (uint32_t)pnx + 1u);  // it / pnx == (it * inv) >> 20 for it < 2^20 / pnx
   }
   __syncthreads();
 
@@ -328,51 +352,88 @@ render_kernel(DevState st, RasterDev rd, uint8_t *__restrict__ frames, int smem_
   __syncthreads();
 
   // ---- phase B: visible segments per canvas row -----------------------------------------
-  // Sprites are taken front to back, in chunks whose crossing lists fit the scratch area.
+  // B1 (sprite, row)-parallel: Pillow's scan conversion of one canvas row of one sprite
+  //    (crossings of the edges that span the row, with the corner-join overrides; sort;
+  //    ROUND_UP/ROUND_DOWN pairing; horizontal edges) -> <= M merged spans.
+  // B2 row-parallel: fold the sprites' spans front to back into the row's visible segments.
+  // Sprites are taken front to back in chunks whose scratch (crossing lists + spans) fits.
   for (int s_hi = S; s_hi > 0;) {
     int s_lo = s_hi, rows_used = 0;
-    while (s_lo > 0 && (s_lo == s_hi || rows_used + s_rcnt[s_lo - 1] <= L.list_rows)) {
-      rows_used += s_rcnt[s_lo - 1];
+    while (s_lo > 0) {
+      const int rows_next = rows_used + s_rcnt[s_lo - 1];
+      const int need = rows_next * CAP * 4 + (s_hi - s_lo + 1) * n_rows * M * 4;
+      if (s_lo != s_hi && need > L.scratch_bytes) break;
+      rows_used = rows_next;
       --s_lo;
     }
+    uint32_t *s_spans = reinterpret_cast<uint32_t *>(smem + L.off_scratch) + rows_used * CAP;
+    const bool fits = rows_used * CAP * 4 + (s_hi - s_lo) * n_rows * M * 4 <= L.scratch_bytes;
+    if (!fits) { s_overflow = 1; }
     if (tid == 0) {
       int off = 0;
       for (int s = s_lo; s < s_hi; ++s) { s_roff[s] = off; off += s_rcnt[s]; }
     }
-    for (int i = tid; i < min(rows_used, L.list_rows); i += R_THREADS) s_lcnt[i] = 0;
     __syncthreads();
-    // B1: edge-parallel crossing insertion
-    for (int t = tid + s_lo * EV; t < s_hi * EV; t += R_THREADS) {
-      if (e_flag[t] != 2) continue;
-      const int s = t / EV;
-      if (s_rcnt[s] == 0) continue;
-      const int r0 = s_r0[s], r1 = r0 + s_rcnt[s] - 1, p_ymax = s_pymax[s];
-      const int ymin = e_ymin[t], ymax = e_ymax[t], y0 = e_y0[t], x0 = e_x0[t];
-      const float dx = e_dx[t], ovs = e_ovs[t], ove = e_ove[t];
-      for (int y = max(ymin, r0); y <= min(ymax, r1); ++y) {
-        float x = edge_x_at(y, y0, dx, x0);
-        if (y == ymin && !isnan(ovs)) x = ovs;
-        if (y == p_ymax && y == ymax && !isnan(ove)) x = ove;
+    // B1
+    for (int t = tid; fits && t < rows_used; t += R_THREADS) {
+      int s = s_lo, rem = t;
+      while (rem >= s_rcnt[s]) { rem -= s_rcnt[s]; ++s; }
+      const int y = s_r0[s] + rem;
+      const int base = s * EV, ne = s_nv[s], p_ymax = s_pymax[s];
+      float *xx = reinterpret_cast<float *>(smem + L.off_scratch) + (size_t)t * CAP;
+      int j = 0;
+      bool ovf = false;
+      for (int i = 0; i < ne; ++i) {
+        const uint32_t yr = e_yr[base + i];
+        const int ymin = (int)(short)(yr & 0xFFFFu), ymax = (int)(short)(yr >> 16);
+        if (y < ymin || y > ymax) continue;
+        const int u = base + i;
+        float x = edge_x_at(y, e_y0[u], e_dx[u], e_x0[u]);
+        if (y == ymin) { const float o = e_ovs[u]; if (!isnan(o)) x = o; }
+        if (y == p_ymax && y == ymax) { const float o = e_ove[u]; if (!isnan(o)) x = o; }
         const int twice = (y == ymax && y < p_ymax) ? 2 : 1;  // edge ending on an interior row
-        const int row = s_roff[s] + (y - r0);
-        if (row < L.list_rows) {
-          const int at = atomicAdd(&s_lcnt[row], twice);
-          if (at + twice <= CAP) {
-            s_list[row * CAP + at] = x;
-            if (twice == 2) s_list[row * CAP + at + 1] = x;
-          } else {
-            s_overflow = 1;
-          }
+        if (j + twice <= CAP) {
+          xx[j] = x;
+          if (twice == 2) xx[j + 1] = x;
+          j += twice;
         } else {
-          s_overflow = 1;
+          ovf = true;
         }
       }
+      for (int a = 1; a < j; ++a) {  // insertion sort, ascending
+        const float v = xx[a];
+        int b = a - 1;
+        while (b >= 0 && xx[b] > v) { xx[b + 1] = xx[b]; --b; }
+        xx[b + 1] = v;
+      }
+      int lxs[MAX_ROW_SPANS], lxe[MAX_ROW_SPANS];
+      int n = 0;
+      int x_pos = 0;
+      for (int i = 1; i < j; i += 2) {
+        const int x_end = round_down_f(xx[i]);
+        if (x_end < x_pos) continue;
+        if (xx[i - 1] > (float)x_pos) {
+          x_pos = round_up_f(xx[i - 1]);
+          if (x_end < x_pos) continue;
+        }
+        const int xs = max(x_pos, 0), xe = min(x_end, rd.CW - 1);
+        if (xs <= xe) add_span(lxs, lxe, n, xs, xe, ovf);
+        x_pos = x_end + 1;
+      }
+      const int nh = s_nh[s];
+      for (int h = 0; h < nh; ++h) {
+        const short *hl = s_hl + ((size_t)s * EV + h) * 3;
+        if (hl[0] == y) add_span(lxs, lxe, n, hl[1], hl[2], ovf);
+      }
+      if (n > M) ovf = true;
+      uint32_t *dst = s_spans + ((size_t)(s - s_lo) * n_rows + (y - row_b0)) * M;
+      for (int k = 0; k < M; ++k)
+        dst[k] = k < n ? ((uint32_t)lxs[k] | ((uint32_t)lxe[k] << 16)) : 0x0000FFFFu;
+      if (ovf) s_overflow = 1;
     }
     __syncthreads();
-    // B2: row-parallel.  For every sprite of the chunk that touches the row, front to back:
-    // sort its crossings, apply Pillow's pairing rule, add horizontal edges, then keep the
-    // parts of its spans that no nearer sprite covers.
-    for (int ry = tid; ry < n_rows; ry += R_THREADS) {
+    // B2
+    for (int ry = tid; fits && ry < n_rows; ry += R_THREADS) {
       const int y = row_b0 + ry;
       uint32_t *seg = s_segs + (size_t)ry * SEGCAP;
       int nseg = s_nseg[ry];
@@ -380,42 +441,13 @@ render_kernel(DevState st, RasterDev rd, uint8_t *__restrict__ frames, int smem_
       for (int s = s_hi - 1; s >= s_lo; --s) {
         const int rem = y - s_r0[s];
         if (rem < 0 || rem >= s_rcnt[s]) continue;
-        const int row = s_roff[s] + rem;
-        int lxs[MAX_ROW_SPANS], lxe[MAX_ROW_SPANS];
-        int n = 0;
-        if (row < L.list_rows) {
-          float *xx = s_list + row * CAP;
-          const int j = min(s_lcnt[row], CAP);
-          for (int a = 1; a < j; ++a) {  // insertion sort, ascending
-            const float v = xx[a];
-            int b = a - 1;
-            while (b >= 0 && xx[b] > v) { xx[b + 1] = xx[b]; --b; }
-            xx[b + 1] = v;
-          }
-          int x_pos = 0;
-          for (int i = 1; i < j; i += 2) {
-            const int x_end = round_down_f(xx[i]);
-            if (x_end < x_pos) continue;
-            if (xx[i - 1] > (float)x_pos) {
-              x_pos = round_up_f(xx[i - 1]);
-              if (x_end < x_pos) continue;
-            }
-            const int xs = max(x_pos, 0), xe = min(x_end, rd.CW - 1);
-            if (xs <= xe) add_span(lxs, lxe, n, xs, xe, ovf);
-            x_pos = x_end + 1;
-          }
-        }
-        const int nh = s_nh[s];
-        for (int h = 0; h < nh; ++h) {
-          const short *hl = s_hl + ((size_t)s * EV + h) * 3;
-          if (hl[0] == y) add_span(lxs, lxe, n, hl[1], hl[2], ovf);
-        }
-        // fold: the sprite's spans minus what is already covered, kept sorted by x
-        for (int k = 0; k < n; ++k) {
-          const int b = lxe[k];
-          int cursor = lxs[k];
+        const uint32_t *spn = s_spans + ((size_t)(s - s_lo) * n_rows + ry) * M;
+        for (int k = 0; k < M; ++k) {
+          const uint32_t w = spn[k];
+          const int b = (int)(w >> 16);
+          int cursor = (int)(w & 0xFFFFu);
+          // the span minus what nearer sprites already cover, kept sorted by x
           for (int i = 0; i <= nseg && cursor <= b; ++i) {
-            // gap before segment i (or after the last one)
             int gap_end = b;
             int next_cursor = b + 1;
             if (i < nseg) {
@@ -469,21 +501,16 @@ render_kernel(DevState st, RasterDev rd, uint8_t *__restrict__ frames, int smem_
     const int ryo0 = s_region[s * 4 + 0], ryo1 = s_region[s * 4 + 1];
     const int rxo0 = s_region[s * 4 + 2], rxo1 = s_region[s * 4 + 3];
     if (ryo1 < ryo0 || rxo1 < rxo0) continue;
-    const int rh = ryo1 - ryo0 + 1, rw = rxo1 - rxo0 + 1;
-    const int nty = (rh + TILE_Y_MAX - 1) / TILE_Y_MAX;
-    const int ny_blk = (rh + nty - 1) / nty;
+    const int ny_blk = s_pny[s], nx_blk = s_pnx[s];
     for (int ty0 = ryo0; ty0 <= ryo1; ty0 += ny_blk) {
       const int ny = min(ny_blk, ryo1 - ty0 + 1);
       const uint32_t yw0 = s_ywin[ty0 - yo_b0], yw1 = s_ywin[ty0 + ny - 1 - yo_b0];
       const int tr0 = (int)(int16_t)(yw0 & 0xFFFFu);
       const int tr1 = (int)(int16_t)(yw1 & 0xFFFFu) + (int)((yw1 >> 16) & 0xFFu);  // exclusive
       const int nr = tr1 - tr0;
-      const int nx_cap = max(1, min(TILE_X_MAX, HT_ITEMS / nr));
-      const int ntx = (rw + nx_cap - 1) / nx_cap;
-      const int nx_blk = (rw + ntx - 1) / ntx;
       for (int tx0 = rxo0; tx0 <= rxo1; tx0 += nx_blk) {
         const int nx = min(nx_blk, rxo1 - tx0 + 1);
-        const uint32_t inv_nx = (1u << 20) / (uint32_t)nx + 1u;  // exact for it < 2^20 / nx
+        const uint32_t inv_nx = nx == nx_blk ? (uint32_t)s_pinv[s] : (1u << 20) / (uint32_t)nx + 1u;
         // ---- H pass: item = (canvas row r, column c), rows of one warp are adjacent ----
         for (int it = tid; it < nr * nx; it += R_THREADS) {
           const int r = (int)(((uint32_t)it * inv_nx) >> 20);
@@ -503,10 +530,10 @@ render_kernel(DevState st, RasterDev rd, uint8_t *__restrict__ frames, int smem_
               const int a = min(max((int)(w & 0xFFFu) - xmin, 0), len);
               const int b = min(max((int)((w >> 12) & 0xFFFu) + 1 - xmin, 0), len);
               const int wt = P[b] - P[a];
-              const uint32_t col = (uint32_t)s_rgb[w >> 24];
-              ar += ((int)(col & 255u) - bg_r) * wt;
-              ag += ((int)((col >> 8) & 255u) - bg_g) * wt;
-              ab += ((int)((col >> 16) & 255u) - bg_b) * wt;
+              const int sp = (int)(w >> 24);
+              ar += s_dr[sp] * wt;
+              ag += s_dg[sp] * wt;
+              ab += s_db[sp] * wt;
             }
             hval = make_uint2(clip8_q22(ar + (1 << 21)) | (clip8_q22(ag + (1 << 21)) << 16),
                               clip8_q22(ab + (1 << 21)));

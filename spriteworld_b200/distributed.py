@@ -43,11 +43,21 @@ class StepGatherer(object):
     self.success = torch.empty(E, dtype=torch.uint8, device=device)
 
   def _gather(self, out, local):
+    local = local.contiguous()
     if self.equal:
-      dist.all_gather_into_tensor(out, local.contiguous(), group=self.group)
-    else:
-      parts = list(torch.split(out, self.sizes, dim=0))
-      dist.all_gather(parts, local.contiguous(), group=self.group)
+      dist.all_gather_into_tensor(out, local, group=self.group)
+      return
+    # uneven shards: collectives want equal sizes, so pad every rank's block to the largest
+    big = max(self.sizes)
+    padded = torch.zeros((big,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    padded[:local.shape[0]] = local
+    buf = torch.empty((self.world * big,) + tuple(local.shape[1:]), dtype=local.dtype,
+                      device=local.device)
+    dist.all_gather_into_tensor(buf, padded, group=self.group)
+    start = 0
+    for r, n in enumerate(self.sizes):
+      out[start:start + n] = buf[r * big:r * big + n]
+      start += n
 
   def gather(self, frames, reward, step_type, success):
     """Every rank receives every env's outputs, ordered by global env index."""

@@ -18,6 +18,14 @@ def _as_ptr(a):
   return ctypes.c_void_p(a.ctypes.data)
 
 
+class _DevicePointer(object):
+  """Minimal __cuda_array_interface__ carrier so torch can alias engine-owned memory."""
+
+  def __init__(self, ptr, shape, typestr):
+    self.__cuda_array_interface__ = dict(shape=tuple(shape), typestr=typestr,
+                                         data=(int(ptr), False), version=2)
+
+
 class StepResult(object):
   """Per-env outputs of one step, as device tensors (valid until the next step)."""
   __slots__ = ('reward', 'step_type', 'success', 'status', 'frames')
@@ -232,6 +240,19 @@ class Engine(object):
     k4, a4 = p(step_count, np.int32)
     k5, a5 = p(reset_next, np.uint8)
     _native.check(self._lib.swb_upload_state(self._h, a1, a2, a3, a4, a5, self._stream()))
+
+  def state_tensors(self):
+    """Zero-copy torch views of the live device state: pos_x/pos_y (E, S) float64,
+    cursor/step_count (E,) int32, reset_next (E,) uint8."""
+    ptrs = [ctypes.c_void_p() for _ in range(5)]
+    _native.check(self._lib.swb_state_pointers(self._h, *[ctypes.byref(p) for p in ptrs]))
+    E, S = self.n_envs, self.n_slots
+    spec = [('pos_x', (E, S), '<f8'), ('pos_y', (E, S), '<f8'), ('cursor', (E,), '<i4'),
+            ('step_count', (E,), '<i4'), ('reset_next', (E,), '|u1')]
+    out = {}
+    for (name, shape, typestr), ptr in zip(spec, ptrs):
+      out[name] = torch.as_tensor(_DevicePointer(ptr.value, shape, typestr), device=self.device)
+    return out
 
   def launch_count(self):
     return int(self._lib.swb_launch_count(self._h))

@@ -279,7 +279,37 @@ class BatchedEnvironment(object):
     batch = scene.arrays_from_layout(layout, self._engine.n_slots, self._filters,
                                      self._color_to_rgb)
     self._engine.upload_scenes(batch, env_ids, ring_slots)
+    if self._other:   # static factors of the pooled scenes, for factor observations
+      E, K, S = self.n_envs, self._K, self._engine.n_slots
+      if getattr(self, '_pool_static', None) is None:
+        self._pool_static = torch.zeros((E, K, S, 8), dtype=torch.float32,
+                                        device=self._engine.device)
+      static = np.concatenate([batch['shape'][..., None].astype(np.float32), batch['factors'],
+                               batch['vx'][..., None].astype(np.float32),
+                               batch['vy'][..., None].astype(np.float32)], -1)
+      e = torch.as_tensor(np.asarray(env_ids), device=self._engine.device, dtype=torch.long)
+      k = torch.as_tensor(np.asarray(ring_slots), device=self._engine.device, dtype=torch.long)
+      self._pool_static[e, k] = torch.from_numpy(static).to(self._engine.device)
     return batch
+
+  _STATIC_COLUMNS = {'shape': 0, 'scale': 1, 'angle': 2, 'c0': 3, 'c1': 4, 'c2': 5,
+                     'x_vel': 6, 'y_vel': 7}
+
+  def factor_tensors(self, factors):
+    """dict factor name -> float32 (n_envs, n_slots) tensor of the current scenes + 'mask'."""
+    live = self._engine.state_tensors()
+    rows = torch.arange(self.n_envs, device=self._engine.device)
+    static = self._pool_static[rows, live['cursor'].long()]      # (E, S, 8)
+    out = collections.OrderedDict()
+    for name in factors:
+      if name == 'x':
+        out[name] = live['pos_x'].to(torch.float32)
+      elif name == 'y':
+        out[name] = live['pos_y'].to(torch.float32)
+      else:
+        out[name] = static[..., self._STATIC_COLUMNS[name]]
+    out['mask'] = static[..., 0] > 0
+    return out
 
   def _refill(self):
     """Re-samples the ring slots the device has consumed since the last check."""

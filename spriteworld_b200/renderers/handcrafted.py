@@ -49,6 +49,11 @@ class SpriteFactors(abstract_renderer.AbstractRenderer):
   def observation_spec(self):
     return [self._per_object_spec for _ in range(self._num_sprites)]
 
+  def render_batch(self, env, res):
+    """Batched form: dict factor -> float32 (n_envs, n_slots) device tensor, plus 'mask'
+    (slot occupied).  Empty slots are padded at the front (the last slot is top-most)."""
+    return env.factor_tensors(self._factors)
+
 
 class Success(abstract_renderer.AbstractRenderer):
   """global_state['success'] as an observation."""
@@ -58,6 +63,9 @@ class Success(abstract_renderer.AbstractRenderer):
 
   def render(self, sprites=(), global_state=None):
     return global_state['success']
+
+  def render_batch(self, env, res):
+    return res.success.to(bool)
 
   def observation_spec(self):
     return self._observation_spec
