@@ -66,6 +66,9 @@ struct swb_engine {
   swb_step_out h_out = {nullptr, nullptr, nullptr, nullptr};
   uint8_t *h_frames = nullptr;
   size_t h_frames_bytes = 0;
+  cudaStream_t copy_stream = nullptr;  // D2H of frame chunks overlaps the render of the next chunk
+  cudaEvent_t chunk_done[8] = {};
+  cudaEvent_t copies_done = nullptr;
 };
 
 struct swb_raster {
@@ -231,6 +234,9 @@ void swb_engine_destroy(swb_engine *eng) {
   cudaFree(eng->g_factors); cudaFree(eng->g_dst);
   cudaFree(eng->h_actions); cudaFree(eng->h_out.reward); cudaFree(eng->h_out.step_type);
   cudaFree(eng->h_out.success); cudaFree(eng->h_out.status); cudaFree(eng->h_frames);
+  if (eng->copy_stream) cudaStreamDestroy(eng->copy_stream);
+  for (auto &ev : eng->chunk_done) if (ev) cudaEventDestroy(ev);
+  if (eng->copies_done) cudaEventDestroy(eng->copies_done);
   if (g_cfg_owner == eng) g_cfg_owner = nullptr;
   delete eng;
 }
@@ -402,7 +408,7 @@ void swb_raster_destroy(swb_raster *r) {
 }
 
 static int launch_render(swb_engine *eng, swb_raster *r, uint8_t *frames, uint8_t *status,
-                         cudaStream_t stream) {
+                         cudaStream_t stream, int env_base = 0, int env_count = -1) {
   if (r->eng != eng) return fail("raster belongs to another engine");
   RasterDev rd = r->rd;
   rd.max_spans = eng->max_spans;
@@ -419,8 +425,10 @@ static int launch_render(swb_engine *eng, swb_raster *r, uint8_t *frames, uint8_
   CUDA_TRY(cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
   DevState st = eng->st;
   st.render_status = status;
-  dim3 grid(eng->st.E, rd.n_bands);
-  render_kernel<<<grid, R_THREADS, L.total, stream>>>(st, rd, frames, r->smem_rows);
+  if (env_count < 0) env_count = eng->st.E - env_base;
+  if (env_count <= 0) return 0;
+  dim3 grid(env_count, rd.n_bands);
+  render_kernel<<<grid, R_THREADS, L.total, stream>>>(st, rd, frames, r->smem_rows, env_base);
   eng->launches++;
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -467,8 +475,30 @@ int swb_step_host(swb_engine *eng, swb_raster *r, const void *actions, int32_t a
       CUDA_TRY(cudaMalloc(&eng->h_frames, fbytes));
       eng->h_frames_bytes = fbytes;
     }
-    if (swb_step_render(eng, r, eng->h_actions, action_dtype, &eng->h_out, eng->h_frames, stream)) return 1;
-    if (frames) CUDA_TRY(cudaMemcpyAsync(frames, eng->h_frames, fbytes, cudaMemcpyDeviceToHost, stream));
+    if (swb_step(eng, eng->h_actions, action_dtype, &eng->h_out, stream)) return 1;
+    if (!frames) {
+      if (launch_render(eng, r, eng->h_frames, eng->h_out.status, stream)) return 1;
+    } else {
+      // render in env chunks; each chunk's frames go to the host on a second stream while
+      // the next chunk renders
+      if (!eng->copy_stream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&eng->copy_stream, cudaStreamNonBlocking));
+        for (auto &ev : eng->chunk_done) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&eng->copies_done, cudaEventDisableTiming));
+      }
+      const size_t per_env = (size_t)r->rd.H * r->rd.W * 3;
+      const int n_chunks = E >= 1024 ? 8 : (E >= 64 ? 2 : 1);
+      for (int c = 0; c < n_chunks; ++c) {
+        const int e0 = (int)((int64_t)E * c / n_chunks), e1 = (int)((int64_t)E * (c + 1) / n_chunks);
+        if (launch_render(eng, r, eng->h_frames, eng->h_out.status, stream, e0, e1 - e0)) return 1;
+        CUDA_TRY(cudaEventRecord(eng->chunk_done[c], stream));
+        CUDA_TRY(cudaStreamWaitEvent(eng->copy_stream, eng->chunk_done[c], 0));
+        CUDA_TRY(cudaMemcpyAsync(frames + per_env * e0, eng->h_frames + per_env * e0, per_env * (e1 - e0),
+                                 cudaMemcpyDeviceToHost, eng->copy_stream));
+      }
+      CUDA_TRY(cudaEventRecord(eng->copies_done, eng->copy_stream));
+      CUDA_TRY(cudaStreamWaitEvent(stream, eng->copies_done, 0));
+    }
   } else {
     if (swb_step(eng, eng->h_actions, action_dtype, &eng->h_out, stream)) return 1;
   }

@@ -115,9 +115,9 @@ __device__ __forceinline__ void add_span(int *lxs, int *lxe, int &n, int xs, int
 }
 
 __global__ void __launch_bounds__(R_THREADS)
-render_kernel(DevState st, RasterDev rd, uint8_t *__restrict__ frames, int smem_rows) {
+render_kernel(DevState st, RasterDev rd, uint8_t *__restrict__ frames, int smem_rows, int env_base) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const int e = blockIdx.x;
+  const int e = env_base + blockIdx.x;  // frames is indexed by the absolute env id
   const int band = blockIdx.y;
   const int tid = threadIdx.x;
   const int S = st.S;
@@ -321,10 +321,11 @@ render_kernel(DevState st, RasterDev rd, uint8_t *__restrict__ frames, int smem_
       const float x = edge_x_at(y, e_y0[t], dx, e_x0[t]);
       for (int k = 0; k < i; ++k) {
         const int u = base + k;
+        const uint32_t yr = e_yr[u];  // empty range for edges that are not scanned
+        if ((pass == 0 ? (int)(short)(yr & 0xFFFFu) : (int)(short)(yr >> 16)) != y) continue;
         if (e_flag[u] != 2) continue;
         const float odx = e_dx[u];
         if ((dx > 0.0f && odx <= 0.0f) || (dx < 0.0f && odx >= 0.0f)) continue;
-        if ((pass == 0 ? e_ymin[u] : e_ymax[u]) != y) continue;
         const float ox = edge_x_at(y, e_y0[u], odx, e_x0[u]);
         if (roundf(x) != roundf(ox)) continue;
         const int off = (y == p_ymax) ? -1 : 1;
@@ -406,29 +407,56 @@ render_kernel(DevState st, RasterDev rd, uint8_t *__restrict__ frames, int smem_
         while (b >= 0 && xx[b] > v) { xx[b + 1] = xx[b]; --b; }
         xx[b + 1] = v;
       }
-      int lxs[MAX_ROW_SPANS], lxe[MAX_ROW_SPANS];
-      int n = 0;
-      int x_pos = 0;
-      for (int i = 1; i < j; i += 2) {
-        const int x_end = round_down_f(xx[i]);
-        if (x_end < x_pos) continue;
-        if (xx[i - 1] > (float)x_pos) {
-          x_pos = round_up_f(xx[i - 1]);
-          if (x_end < x_pos) continue;
-        }
-        const int xs = max(x_pos, 0), xe = min(x_end, rd.CW - 1);
-        if (xs <= xe) add_span(lxs, lxe, n, xs, xe, ovf);
-        x_pos = x_end + 1;
-      }
-      const int nh = s_nh[s];
-      for (int h = 0; h < nh; ++h) {
-        const short *hl = s_hl + ((size_t)s * EV + h) * 3;
-        if (hl[0] == y) add_span(lxs, lxe, n, hl[1], hl[2], ovf);
-      }
-      if (n > M) ovf = true;
       uint32_t *dst = s_spans + ((size_t)(s - s_lo) * n_rows + (y - row_b0)) * M;
-      for (int k = 0; k < M; ++k)
-        dst[k] = k < n ? ((uint32_t)lxs[k] | ((uint32_t)lxe[k] << 16)) : 0x0000FFFFu;
+      const int nh = s_nh[s];
+      if (M == 1) {
+        // convex shapes: every span of the row merges into one [lo, hi] (kept in registers)
+        int lo = 1, hi = 0;
+        auto merge1 = [&](int xs, int xe) {
+          if (lo > hi) { lo = xs; hi = xe; }
+          else if (xs <= hi + 1 && lo <= xe + 1) { lo = min(lo, xs); hi = max(hi, xe); }
+          else ovf = true;  // a second, disjoint span: the engine was sized for convex shapes
+        };
+        int x_pos = 0;
+        for (int i = 1; i < j; i += 2) {
+          const int x_end = round_down_f(xx[i]);
+          if (x_end < x_pos) continue;
+          if (xx[i - 1] > (float)x_pos) {
+            x_pos = round_up_f(xx[i - 1]);
+            if (x_end < x_pos) continue;
+          }
+          const int xs = max(x_pos, 0), xe = min(x_end, rd.CW - 1);
+          if (xs <= xe) merge1(xs, xe);
+          x_pos = x_end + 1;
+        }
+        for (int h = 0; h < nh; ++h) {
+          const short *hl = s_hl + ((size_t)s * EV + h) * 3;
+          if (hl[0] == y) merge1(hl[1], hl[2]);
+        }
+        dst[0] = lo <= hi ? ((uint32_t)lo | ((uint32_t)hi << 16)) : 0x0000FFFFu;
+      } else {
+        int lxs[MAX_ROW_SPANS], lxe[MAX_ROW_SPANS];
+        int n = 0;
+        int x_pos = 0;
+        for (int i = 1; i < j; i += 2) {
+          const int x_end = round_down_f(xx[i]);
+          if (x_end < x_pos) continue;
+          if (xx[i - 1] > (float)x_pos) {
+            x_pos = round_up_f(xx[i - 1]);
+            if (x_end < x_pos) continue;
+          }
+          const int xs = max(x_pos, 0), xe = min(x_end, rd.CW - 1);
+          if (xs <= xe) add_span(lxs, lxe, n, xs, xe, ovf);
+          x_pos = x_end + 1;
+        }
+        for (int h = 0; h < nh; ++h) {
+          const short *hl = s_hl + ((size_t)s * EV + h) * 3;
+          if (hl[0] == y) add_span(lxs, lxe, n, hl[1], hl[2], ovf);
+        }
+        if (n > M) ovf = true;
+        for (int k = 0; k < M; ++k)
+          dst[k] = k < n ? ((uint32_t)lxs[k] | ((uint32_t)lxe[k] << 16)) : 0x0000FFFFu;
+      }
       if (ovf) s_overflow = 1;
     }
     __syncthreads();
@@ -511,34 +539,41 @@ render_kernel(DevState st, RasterDev rd, uint8_t *__restrict__ frames, int smem_
       for (int tx0 = rxo0; tx0 <= rxo1; tx0 += nx_blk) {
         const int nx = min(nx_blk, rxo1 - tx0 + 1);
         const uint32_t inv_nx = nx == nx_blk ? (uint32_t)s_pinv[s] : (1u << 20) / (uint32_t)nx + 1u;
-        // ---- H pass: item = (canvas row r, column c), rows of one warp are adjacent ----
-        for (int it = tid; it < nr * nx; it += R_THREADS) {
-          const int r = (int)(((uint32_t)it * inv_nx) >> 20);
-          const int c = it - r * nx;
-          const int ry = tr0 + r - row_b0;
-          const int nseg = s_nseg[ry];
-          uint2 hval = bg_h;
-          if (nseg) {
+        // ---- H pass: a thread keeps its column c and strides over the canvas rows, so the
+        // window start/length, tap prefix table and bg*K are loop invariants ----
+        {
+          const int rgroup = (int)(((uint32_t)tid * inv_nx) >> 20);  // tid / nx
+          const int c = tid - rgroup * nx;
+          const int rstride = R_THREADS / nx;                       // row groups per pass
+          if (rgroup < rstride) {
             const uint32_t xw = s_xwin[tx0 + c];
             const int xmin = (int)(int16_t)(xw & 0xFFFFu), len = (int)((xw >> 16) & 0xFFu);
             const int32_t *P = s_prefix + (int)(xw >> 24) * 33;
             const int ktot = P[len];
-            const uint32_t *seg = s_segs + (size_t)ry * SEGCAP;
-            int ar = bg_r * ktot, ag = bg_g * ktot, ab = bg_b * ktot;
-            for (int j = 0; j < nseg; ++j) {
-              const uint32_t w = seg[j];
-              const int a = min(max((int)(w & 0xFFFu) - xmin, 0), len);
-              const int b = min(max((int)((w >> 12) & 0xFFFu) + 1 - xmin, 0), len);
-              const int wt = P[b] - P[a];
-              const int sp = (int)(w >> 24);
-              ar += s_dr[sp] * wt;
-              ag += s_dg[sp] * wt;
-              ab += s_db[sp] * wt;
+            const int base_r = bg_r * ktot + (1 << 21), base_g = bg_g * ktot + (1 << 21),
+                      base_b = bg_b * ktot + (1 << 21);
+            for (int r = rgroup; r < nr; r += rstride) {
+              const int ry = tr0 + r - row_b0;
+              const int nseg = s_nseg[ry];
+              uint2 hval = bg_h;
+              if (nseg) {
+                const uint32_t *seg = s_segs + (size_t)ry * SEGCAP;
+                int ar = base_r, ag = base_g, ab = base_b;
+                for (int j = 0; j < nseg; ++j) {
+                  const uint32_t w = seg[j];
+                  const int a = min(max((int)(w & 0xFFFu) - xmin, 0), len);
+                  const int b = min(max((int)((w >> 12) & 0xFFFu) + 1 - xmin, 0), len);
+                  const int wt = P[b] - P[a];
+                  const int sp = (int)(w >> 24);
+                  ar += s_dr[sp] * wt;
+                  ag += s_dg[sp] * wt;
+                  ab += s_db[sp] * wt;
+                }
+                hval = make_uint2(clip8_q22(ar) | (clip8_q22(ag) << 16), clip8_q22(ab));
+              }
+              s_ht[r * nx + c] = hval;
             }
-            hval = make_uint2(clip8_q22(ar + (1 << 21)) | (clip8_q22(ag + (1 << 21)) << 16),
-                              clip8_q22(ab + (1 << 21)));
           }
-          s_ht[it] = hval;
         }
         __syncthreads();
         // ---- V pass: item = (output row ly, column c) ----
@@ -552,25 +587,41 @@ render_kernel(DevState st, RasterDev rd, uint8_t *__restrict__ frames, int smem_
           const int np = prog[0], ns = prog[1];
           int ar = 1 << 21, ag = 1 << 21, ab = 1 << 21;
           const int2 *pp = reinterpret_cast<const int2 *>(prog + 2);
-          const uint2 *col_ht = s_ht + rbase * nx + c;
-#pragma unroll 4
-          for (int k = 0; k < np; ++k) {
-            const int2 pk = pp[k];  // (row a | row b << 8, coefficient)
-            const uint2 u = col_ht[(pk.x & 255) * nx];
-            const uint2 v = col_ht[(pk.x >> 8) * nx];
-            const uint32_t rg = u.x + v.x, bb = u.y + v.y;
-            ar += (int)(rg & 0xFFFFu) * pk.y;
-            ag += (int)(rg >> 16) * pk.y;
-            ab += (int)bb * pk.y;
-          }
           const int2 *ps = reinterpret_cast<const int2 *>(prog + 2 + 2 * 16);
-#pragma unroll 2
-          for (int k = 0; k < ns; ++k) {
-            const int2 pk = ps[k];
+          const uint2 *col_ht = s_ht + rbase * nx + c;
+          if (np == 12 && ns == 1) {  // interior rows at anti_aliasing 5: fixed trip counts
+#pragma unroll
+            for (int k = 0; k < 12; ++k) {
+              const int2 pk = pp[k];
+              const uint2 u = col_ht[(pk.x & 255) * nx];
+              const uint2 v = col_ht[(pk.x >> 8) * nx];
+              const uint32_t rg = u.x + v.x, bb = u.y + v.y;
+              ar += (int)(rg & 0xFFFFu) * pk.y;
+              ag += (int)(rg >> 16) * pk.y;
+              ab += (int)bb * pk.y;
+            }
+            const int2 pk = ps[0];
             const uint2 u = col_ht[pk.x * nx];
             ar += (int)(u.x & 0xFFFFu) * pk.y;
             ag += (int)(u.x >> 16) * pk.y;
             ab += (int)u.y * pk.y;
+          } else {
+            for (int k = 0; k < np; ++k) {
+              const int2 pk = pp[k];  // (row a | row b << 8, coefficient)
+              const uint2 u = col_ht[(pk.x & 255) * nx];
+              const uint2 v = col_ht[(pk.x >> 8) * nx];
+              const uint32_t rg = u.x + v.x, bb = u.y + v.y;
+              ar += (int)(rg & 0xFFFFu) * pk.y;
+              ag += (int)(rg >> 16) * pk.y;
+              ab += (int)bb * pk.y;
+            }
+            for (int k = 0; k < ns; ++k) {
+              const int2 pk = ps[k];
+              const uint2 u = col_ht[pk.x * nx];
+              ar += (int)(u.x & 0xFFFFu) * pk.y;
+              ag += (int)(u.x >> 16) * pk.y;
+              ab += (int)u.y * pk.y;
+            }
           }
           uint8_t *px = s_frame + ((size_t)(yo - yo_b0) * rd.W + tx0 + c) * 3;
           px[0] = (uint8_t)clip8_q22(ar);

@@ -350,3 +350,37 @@ def test_batched_environment_matches_oracle_with_pool_refill():
     assert ts.discount.dtype == torch.float32
   assert n_first > E            # auto-resets happened beyond the initial one
   env.close()
+
+
+def test_batched_factor_observations_and_gym_surface():
+  """SpriteFactors / Success in batched form and the gym-style wrappers."""
+  import torch
+  from spriteworld_b200 import environment, gym_wrapper, renderers
+  from spriteworld_b200.configs.cobra import goal_finding_more_targets as cfgmod
+  cfg = cfgmod.get_config('test')
+  cfg['renderers'] = dict(cfg['renderers'], factors=renderers.SpriteFactors(),
+                          success=renderers.Success())
+  env = environment.BatchedEnvironment(n_envs=64, pool_depth=4, rng=np.random.RandomState(0), **cfg)
+  venv = gym_wrapper.VectorGymWrapper(env)
+  obs = venv.reset()
+  assert obs['image'].shape == (64, 64, 64, 3) and obs['image'].dtype == torch.uint8
+  f = obs['factors']
+  assert f['mask'].all() and f['x'].shape == (64, 4)
+  state = env.engine.download_state()
+  assert np.array_equal(f['x'].cpu().numpy(), state['pos_x'].astype(np.float32))
+  assert ((f['shape'] >= 1) & (f['shape'] <= 6)).all()
+  assert torch.allclose(f['scale'], torch.full_like(f['scale'], 0.13))
+  assert obs['success'].dtype == torch.bool
+  a = torch.rand(64, 4, device=env.engine.device)
+  obs, reward, done, info = venv.step(a)
+  assert reward.shape == (64,) and done.dtype == torch.bool and not info['first'].any()
+  venv.close()
+  # single-env gym wrapper (reference gym_wrapper.py:91-109 semantics)
+  env1 = environment.Environment(**cfgmod.get_config('test'))
+  g = gym_wrapper.GymWrapper(env1)
+  o = g.reset()
+  assert o['image'].shape == (64, 64, 3)
+  o, r, d, info = g.step(g.action_space.sample())
+  assert isinstance(d, bool) and info['discount'] in (0.0, 1.0)
+  assert np.array_equal(g.render(), o['image'])
+  g.close()
