@@ -165,17 +165,32 @@ def main():
   # frame ring larger than L2 (126 MB) so that every step's frame writes reach HBM
   n_ring = max(2, int(np.ceil(160e6 / frame_bytes)) + 1)
   ring = [raster.new_frames() for _ in range(n_ring)]
-  gathered = None
-  if world > 1:
-    gathered = torch.empty((world * E, H, W, 3), dtype=torch.uint8, device=dev)
+  gathered, inflight = None, []   # inflight: (work handle, ring slot read, gather buffer written)
+  if world > 1:   # double-buffered destination of the per-step frame gather
+    gathered = [torch.empty((world * E, H, W, 3), dtype=torch.uint8, device=dev) for _ in range(2)]
+
+  def wait_for(pred):
+    for item in list(inflight):
+      if pred(item):
+        item[0].wait()
+        inflight.remove(item)
 
   def one_step(t):
-    fr = ring[t % n_ring]
+    slot, dst = t % n_ring, t % 2
+    wait_for(lambda it: it[1] == slot)     # the gather that last read this ring buffer
+    fr = ring[slot]
     eng.step(actions[t], raster, fr)
-    if world > 1:   # the single collective of the path: gather the rendered frames
-      dist.all_gather_into_tensor(gathered, fr)
+    if world > 1:
+      # the single collective of the path: gather the rendered frames of every rank.  It
+      # runs on NCCL's stream and overlaps the next step's compute.
+      wait_for(lambda it: it[2] == dst)
+      inflight.append((dist.all_gather_into_tensor(gathered[dst], fr, async_op=True), slot, dst))
+
+  def drain():
+    wait_for(lambda it: True)
 
   def barrier():
+    drain()
     if world > 1:
       dist.barrier()
     torch.cuda.synchronize()
@@ -193,6 +208,7 @@ def main():
   ev0.record()
   for t in range(args.warmup, T):
     one_step(t)
+  drain()
   ev1.record()
   barrier()
   ms = ev0.elapsed_time(ev1)
@@ -278,7 +294,7 @@ def main():
                   max_episode_length=wl.max_episode_length, auto_reset='pooled scenes',
                   pool_depth=K, l2='frame ring of %d buffers (%.0f MB) > L2, no flush'
                   % (n_ring, n_ring * frame_bytes / 1e6),
-                  collective='all_gather of frames per step' if world > 1 else 'none'),
+                  collective='all_gather of frames per step (async, overlaps the next step)' if world > 1 else 'none'),
       roofline=dict(bound='hbm', achieved=achieved, peak=peak, unit='GB/s',
                     frac=achieved / peak, traffic=traffic, peak_kind=peak_kind,
                     kernel='render_kernel', kernel_ms=render_ms,

@@ -428,7 +428,7 @@ static int launch_render(swb_engine *eng, swb_raster *r, uint8_t *frames, uint8_
   if (env_count < 0) env_count = eng->st.E - env_base;
   if (env_count <= 0) return 0;
   dim3 grid(env_count, rd.n_bands);
-  render_kernel<<<grid, R_THREADS, L.total, stream>>>(st, rd, frames, r->smem_rows, env_base);
+  render_kernel<<<grid, R_THREADS, L.total, stream>>>(st, rd, L, frames, env_base);
   eng->launches++;
   CUDA_TRY(cudaGetLastError());
   return 0;

@@ -35,9 +35,9 @@
 namespace swb {
 
 constexpr int R_THREADS = 256;
-constexpr int TILE_Y_MAX = 32;    // output rows per tile
-constexpr int TILE_X_MAX = 32;    // output columns per tile
-constexpr int HT_ITEMS = 2560;    // H values a tile may hold (rows x columns)
+constexpr int TILE_X_MAX = 20;    // output columns per tile = row stride of the H buffer
+constexpr int HT_ROWS = 112;      // canvas rows a tile's H buffer holds
+constexpr int HT_ITEMS = HT_ROWS * TILE_X_MAX;
 constexpr int MAX_ROW_SPANS = 12;
 constexpr int EV = SWB_MAX_VERTS;  // edge slots per sprite
 
@@ -55,7 +55,7 @@ struct RenderLayout {
     off_meta = take(S * 20 * 4);
     off_iv = take(S * EV * 2 * 4);
     off_edge_i = take(S * EV * 4 * 4);     // x0, y0, ymin, ymax
-    off_edge_f = take(S * EV * 5 * 4);     // dx, ovs, ove, join nv (start), join nv (end)
+    off_edge_f = take(S * EV * 7 * 4);     // dx, ovs, ove, join nv (start/end), join owner (start/end)
     off_edge_b = take(S * EV * 3);         // flag, join partner (start), join partner (end)
     off_edge_yr = take(S * EV * 4);        // ymin | ymax<<16 of non-horizontal edges, empty otherwise
     off_hl = take(S * EV * 3 * 2);         // horizontal edges: y, xmin, xmax (int16)
@@ -115,13 +115,13 @@ __device__ __forceinline__ void add_span(int *lxs, int *lxe, int &n, int xs, int
 }
 
 __global__ void __launch_bounds__(R_THREADS)
-render_kernel(DevState st, RasterDev rd, uint8_t *__restrict__ frames, int smem_rows, int env_base) {
+render_kernel(DevState st, RasterDev rd, const RenderLayout L, uint8_t *__restrict__ frames,
+              int env_base) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int e = env_base + blockIdx.x;  // frames is indexed by the absolute env id
   const int band = blockIdx.y;
   const int tid = threadIdx.x;
   const int S = st.S;
-  const RenderLayout L(S, smem_rows, rd.max_spans, rd.band_rows, rd.W, rd.aa, rd.ncls_x, rd.ncls_y);
 
   double *s_px = reinterpret_cast<double *>(smem + L.off_pos);
   double *s_py = s_px + S;
@@ -140,6 +140,7 @@ render_kernel(DevState st, RasterDev rd, uint8_t *__restrict__ frames, int smem_
   float *e_dx = reinterpret_cast<float *>(smem + L.off_edge_f);
   float *e_ovs = e_dx + S * EV, *e_ove = e_ovs + S * EV;
   float *e_jvs = e_ove + S * EV, *e_jve = e_jvs + S * EV;
+  int *e_own_s = reinterpret_cast<int *>(e_jve + S * EV), *e_own_e = e_own_s + S * EV;  // latest joiner of k
   uint8_t *e_flag = smem + L.off_edge_b;
   int8_t *e_jks = reinterpret_cast<int8_t *>(e_flag + S * EV);
   int8_t *e_jke = e_jks + S * EV;
@@ -257,6 +258,8 @@ render_kernel(DevState st, RasterDev rd, uint8_t *__restrict__ frames, int smem_
     e_ove[t] = nanf("");
     e_jks[t] = -1;
     e_jke[t] = -1;
+    e_own_s[t] = -1;
+    e_own_e[t] = -1;
   }
   if (tid < S) {
     const int nv = s_nv[tid];
@@ -287,15 +290,15 @@ render_kernel(DevState st, RasterDev rd, uint8_t *__restrict__ frames, int smem_
     }
     s_region[tid * 4 + 0] = yo0; s_region[tid * 4 + 1] = yo1;
     s_region[tid * 4 + 2] = xo0; s_region[tid * 4 + 3] = xo1;
-    // tile plan: ceil(h/32) row blocks; as few equal column blocks as fit HT_ITEMS H values
-    // (columns need no halo, rows do: <= ny*aa + 32 canvas rows per block)
+    // tile plan: equal row blocks whose canvas rows (<= ny*aa + 32) fit the H buffer, equal
+    // column blocks of at most TILE_X_MAX (columns need no halo, rows do)
     int pny = 1, pnx = 1;
     if (yo1 >= yo0 && xo1 >= xo0) {
       const int rh = yo1 - yo0 + 1, rw = xo1 - xo0 + 1;
-      const int nty = (rh + TILE_Y_MAX - 1) / TILE_Y_MAX;
+      const int ny_cap = max(1, (HT_ROWS - 32) / rd.aa + 1);  // (ny-1)*aa + len <= HT_ROWS
+      const int nty = (rh + ny_cap - 1) / ny_cap;
       pny = (rh + nty - 1) / nty;
-      const int nx_cap = max(1, min(TILE_X_MAX, HT_ITEMS / (pny * rd.aa + 32)));
-      const int ntx = (rw + nx_cap - 1) / nx_cap;
+      const int ntx = (rw + TILE_X_MAX - 1) / TILE_X_MAX;
       pnx = (rw + ntx - 1) / ntx;
     }
     s_pny[tid] = pny; s_pnx[tid] = pnx;
@@ -335,20 +338,19 @@ render_kernel(DevState st, RasterDev rd, uint8_t *__restrict__ frames, int smem_
         float nv = right ? __fsub_rn(fminf(adj, adjo), 1.0f) : __fadd_rn(fmaxf(adj, adjo), 1.0f);
         nv = floorf(__fadd_rn(nv, 0.5f));
         nv = right ? fmaxf(nv, x) : fminf(nv, x);
-        if (pass == 0) { e_jks[t] = (int8_t)k; e_jvs[t] = nv; }
-        else { e_jke[t] = (int8_t)k; e_jve[t] = nv; }
+        // several later edges may pick the same k: the last one in table order wins
+        if (pass == 0) { e_jks[t] = (int8_t)k; e_jvs[t] = nv; atomicMax(&e_own_s[base + k], i); }
+        else { e_jke[t] = (int8_t)k; e_jve[t] = nv; atomicMax(&e_own_e[base + k], i); }
         break;
       }
     }
   }
   __syncthreads();
-  for (int t = tid; t < S * EV; t += R_THREADS) {  // the latest edge to pick k wins
-    if (e_flag[t] != 2) continue;
-    const int s = t / EV, k = t % EV, base = s * EV, ne = s_nv[s];
-    for (int i = k + 1; i < ne; ++i) {
-      if (e_jks[base + i] == k) e_ovs[t] = e_jvs[base + i];
-      if (e_jke[base + i] == k) e_ove[t] = e_jve[base + i];
-    }
+  for (int t = tid; t < S * EV; t += R_THREADS) {
+    const int i = t % EV, base = t - i;
+    const int ks = e_jks[t], ke = e_jke[t];
+    if (ks >= 0 && e_own_s[base + ks] == i) e_ovs[base + ks] = e_jvs[t];
+    if (ke >= 0 && e_own_e[base + ke] == i) e_ove[base + ke] = e_jve[t];
   }
   __syncthreads();
 
@@ -571,7 +573,7 @@ render_kernel(DevState st, RasterDev rd, uint8_t *__restrict__ frames, int smem_
                 }
                 hval = make_uint2(clip8_q22(ar) | (clip8_q22(ag) << 16), clip8_q22(ab));
               }
-              s_ht[r * nx + c] = hval;
+              s_ht[r * TILE_X_MAX + c] = hval;
             }
           }
         }
@@ -584,32 +586,35 @@ render_kernel(DevState st, RasterDev rd, uint8_t *__restrict__ frames, int smem_
           const uint32_t yw = s_ywin[yo - yo_b0];
           const int rbase = (int)(int16_t)(yw & 0xFFFFu) - tr0;
           const int32_t *prog = s_prog + (int)(yw >> 24) * PROG_STRIDE;
-          const int np = prog[0], ns = prog[1];
+          const int np = prog[0], ns = prog[1] & 0xFFFF;
           int ar = 1 << 21, ag = 1 << 21, ab = 1 << 21;
           const int2 *pp = reinterpret_cast<const int2 *>(prog + 2);
           const int2 *ps = reinterpret_cast<const int2 *>(prog + 2 + 2 * 16);
-          const uint2 *col_ht = s_ht + rbase * nx + c;
-          if (np == 12 && ns == 1) {  // interior rows at anti_aliasing 5: fixed trip counts
+          const uint2 *col_ht = s_ht + rbase * TILE_X_MAX + c;
+          if (prog[1] >> 16) {
+            // interior rows of a 5x reduction: taps (k, 28-k) pair up, 4/9/19/24/29 are zero,
+            // 14 is the centre -> every load has an immediate offset
+            constexpr int A5[12] = {0, 1, 2, 3, 5, 6, 7, 8, 10, 11, 12, 13};
 #pragma unroll
             for (int k = 0; k < 12; ++k) {
-              const int2 pk = pp[k];
-              const uint2 u = col_ht[(pk.x & 255) * nx];
-              const uint2 v = col_ht[(pk.x >> 8) * nx];
+              const int kk = pp[k].y;
+              const uint2 u = col_ht[A5[k] * TILE_X_MAX];
+              const uint2 v = col_ht[(28 - A5[k]) * TILE_X_MAX];
               const uint32_t rg = u.x + v.x, bb = u.y + v.y;
-              ar += (int)(rg & 0xFFFFu) * pk.y;
-              ag += (int)(rg >> 16) * pk.y;
-              ab += (int)bb * pk.y;
+              ar += (int)(rg & 0xFFFFu) * kk;
+              ag += (int)(rg >> 16) * kk;
+              ab += (int)bb * kk;
             }
-            const int2 pk = ps[0];
-            const uint2 u = col_ht[pk.x * nx];
-            ar += (int)(u.x & 0xFFFFu) * pk.y;
-            ag += (int)(u.x >> 16) * pk.y;
-            ab += (int)u.y * pk.y;
+            const int kk = ps[0].y;
+            const uint2 u = col_ht[14 * TILE_X_MAX];
+            ar += (int)(u.x & 0xFFFFu) * kk;
+            ag += (int)(u.x >> 16) * kk;
+            ab += (int)u.y * kk;
           } else {
             for (int k = 0; k < np; ++k) {
               const int2 pk = pp[k];  // (row a | row b << 8, coefficient)
-              const uint2 u = col_ht[(pk.x & 255) * nx];
-              const uint2 v = col_ht[(pk.x >> 8) * nx];
+              const uint2 u = col_ht[(pk.x & 255) * TILE_X_MAX];
+              const uint2 v = col_ht[(pk.x >> 8) * TILE_X_MAX];
               const uint32_t rg = u.x + v.x, bb = u.y + v.y;
               ar += (int)(rg & 0xFFFFu) * pk.y;
               ag += (int)(rg >> 16) * pk.y;
@@ -617,7 +622,7 @@ render_kernel(DevState st, RasterDev rd, uint8_t *__restrict__ frames, int smem_
             }
             for (int k = 0; k < ns; ++k) {
               const int2 pk = ps[k];
-              const uint2 u = col_ht[pk.x * nx];
+              const uint2 u = col_ht[pk.x * TILE_X_MAX];
               ar += (int)(u.x & 0xFFFFu) * pk.y;
               ag += (int)(u.x >> 16) * pk.y;
               ab += (int)u.y * pk.y;

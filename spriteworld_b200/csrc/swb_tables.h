@@ -9,6 +9,8 @@
 // paired-tap program per class (vertical pass: equal coefficients share a multiply) and
 // the inverse maps "input index -> first/last output whose window contains it".
 #pragma once
+#include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdint>
 #include <map>
@@ -120,29 +122,39 @@ inline bool build_axis(int n_in, int n_out, AxisHost *ax, std::string *err) {
       P[i] = run;
       if (i < (int)t.size()) run += t[i];
     }
-    // paired-tap program: taps with equal non-zero coefficient are added before the multiply
+    // paired-tap program: taps with equal non-zero coefficient are added before the multiply.
+    // Pairs are emitted in ascending order of their first tap.
     int32_t *prog = ax->program.data() + (size_t)kv.second * PROG_STRIDE;
     std::map<int32_t, std::vector<int>> by_coef;
     for (int i = 0; i < (int)t.size(); ++i)
       if (t[i] != 0) by_coef[t[i]].push_back(i);
-    int np = 0, ns = 0;
-    int32_t *pairs = prog + 2, *singles = prog + 2 + 2 * 16;
+    std::vector<std::array<int32_t, 3>> pair_list;  // a, b, coefficient
+    std::vector<std::array<int32_t, 2>> single_list;
     for (const auto &bc : by_coef) {
       const std::vector<int> &idx = bc.second;
       size_t i = 0;
-      for (; i + 1 < idx.size() && np < 16; i += 2) {
-        pairs[2 * np] = idx[i] | (idx[i + 1] << 8);
-        pairs[2 * np + 1] = bc.first;
-        ++np;
-      }
-      for (; i < idx.size(); ++i) {
-        singles[2 * ns] = idx[i];
-        singles[2 * ns + 1] = bc.first;
-        ++ns;
-      }
+      for (; i + 1 < idx.size() && pair_list.size() < 16; i += 2) pair_list.push_back({idx[i], idx[i + 1], bc.first});
+      for (; i < idx.size(); ++i) single_list.push_back({idx[i], bc.first});
     }
-    prog[0] = np;
-    prog[1] = ns;
+    std::sort(pair_list.begin(), pair_list.end());
+    std::sort(single_list.begin(), single_list.end());
+    int32_t *pairs = prog + 2, *singles = prog + 2 + 2 * 16;
+    for (size_t i = 0; i < pair_list.size(); ++i) {
+      pairs[2 * i] = pair_list[i][0] | (pair_list[i][1] << 8);
+      pairs[2 * i + 1] = pair_list[i][2];
+    }
+    for (size_t i = 0; i < single_list.size(); ++i) {
+      singles[2 * i] = single_list[i][0];
+      singles[2 * i + 1] = single_list[i][1];
+    }
+    // the interior vector of a 5x LANCZOS reduction: taps k and 28-k are
+    // equal, taps 4, 9, 19, 24, 29 are zero, tap 14 is the centre.  The kernel has an
+    // unrolled path with immediate offsets for exactly this shape (flag in bit 16 of ns).
+    static const int kA5[12] = {0, 1, 2, 3, 5, 6, 7, 8, 10, 11, 12, 13};
+    bool a5 = pair_list.size() == 12 && single_list.size() == 1 && single_list[0][0] == 14;
+    for (int i = 0; a5 && i < 12; ++i) a5 = pair_list[i][0] == kA5[i] && pair_list[i][1] == 28 - kA5[i];
+    prog[0] = (int32_t)pair_list.size();
+    prog[1] = (int32_t)single_list.size() | (a5 ? (1 << 16) : 0);
   }
   // inverse maps
   ax->first_out.assign(n_in, (int16_t)(n_out - 1));

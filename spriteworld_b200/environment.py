@@ -385,7 +385,9 @@ class BatchedEnvironment(object):
     return self.step(torch.zeros(shape, dtype=dtype, device=self._engine.device))
 
   def observation_spec(self):
-    return {name: r.observation_spec() for name, r in self._renderers.items()}
+    """Per-env specs (the leading n_envs axis of the batched observations is not included)."""
+    return {name: (r.batch_observation_spec(self) if hasattr(r, 'batch_observation_spec')
+                   else r.observation_spec()) for name, r in self._renderers.items()}
 
   def action_spec(self):
     return self._action_space.action_spec()

@@ -54,6 +54,12 @@ class SpriteFactors(abstract_renderer.AbstractRenderer):
     (slot occupied).  Empty slots are padded at the front (the last slot is top-most)."""
     return env.factor_tensors(self._factors)
 
+  def batch_observation_spec(self, env):
+    n = env.engine.n_slots
+    spec = {f: specs.Array(shape=(n,), dtype=np.float32) for f in self._factors}
+    spec['mask'] = specs.Array(shape=(n,), dtype=bool)
+    return spec
+
 
 class Success(abstract_renderer.AbstractRenderer):
   """global_state['success'] as an observation."""
