@@ -387,6 +387,15 @@ int swb_raster_create(swb_engine *eng, int32_t width, int32_t height, int32_t aa
   rd.max_spans = 1;
   rd.ncls_x = r->ax.n_cls;
   rd.ncls_y = r->ay.n_cls;
+  rd.a5_cls = -1;
+  for (int c = 0; c < r->ay.n_cls; ++c) {
+    const int32_t *prog = r->ay.program.data() + (size_t)c * PROG_STRIDE;
+    if (prog[1] >> 16) {
+      rd.a5_cls = c;
+      for (int k = 0; k < 12; ++k) rd.a5_coef[k] = prog[2 + 2 * k + 1];
+      rd.a5_coef[12] = prog[2 + 2 * 16 + 1];
+    }
+  }
   int rows = 0;
   for (int b = 0; b < rd.n_bands; ++b) {
     const int y0 = b * rd.band_rows, y1 = std::min(y0 + rd.band_rows, height) - 1;

@@ -44,7 +44,7 @@ constexpr int EV = SWB_MAX_VERTS;  // edge slots per sprite
 struct RenderLayout {
   int S, rows, M, band_rows, W, aa, ncx, ncy, cap;
   int off_pos, off_meta, off_iv, off_edge_i, off_edge_f, off_edge_b, off_edge_yr, off_hl, off_region;
-  int off_nseg, off_segs, off_prefix, off_prog, off_xwin, off_ywin, off_scratch, off_frame, total;
+  int off_nseg, off_segs, off_prefix, off_xwin, off_ywin, off_scratch, off_frame, total;
   int scratch_bytes, list_rows, segcap;
   __host__ __device__ RenderLayout(int S_, int rows_, int M_, int band_rows_, int W_, int aa_,
                                    int ncx_, int ncy_)
@@ -64,15 +64,20 @@ struct RenderLayout {
     off_nseg = take(rows);
     off_segs = take(rows * segcap * 4);
     off_prefix = take(ncx * 33 * 4);
-    off_prog = take(ncy * PROG_STRIDE * 4);
     off_xwin = take(W * 4);                // per output column: win_min | len<<16 | cls<<24
     off_ywin = take(band_rows * 4);
     // scratch: H tile + staged frame; phase B aliases it with the per-row crossing lists
-    off_scratch = take(HT_ITEMS * 8);
-    off_frame = take(band_rows * W * 3);
+    cap = (M > 1) ? 16 : 8;                // crossings kept per (sprite, row)
+    // scratch = H tile + staged frame; phase B aliases it with the per-row crossing lists and
+    // spans of a chunk of sprites, so it must hold at least one sprite spanning every row
+    const int frame_bytes = band_rows * W * 3;
+    const int need_b = (cap + M) * 4 * rows;
+    int ht_bytes = HT_ITEMS * 4;           // one H value = r | g<<10 | b<<20
+    if (ht_bytes + ((frame_bytes + 15) & ~15) < need_b) ht_bytes = need_b - frame_bytes;
+    off_scratch = take(ht_bytes);
+    off_frame = take(frame_bytes);
     total = o;
     scratch_bytes = total - off_scratch;
-    cap = (M > 1) ? 16 : 8;                // crossings kept per (sprite, row)
     list_rows = scratch_bytes / (cap * 4 + 4);  // upper bound; phase B sizes its chunks itself
   }
 };
@@ -86,9 +91,16 @@ __device__ __forceinline__ int round_down_f(float f) {
 __device__ __forceinline__ float edge_x_at(int y, int y0, float dx, int x0) {
   return __fadd_rn(__fmul_rn((float)(y - y0), dx), (float)x0);
 }
-__device__ __forceinline__ uint32_t clip8_q22(int v) {
-  v >>= 22;
-  return (uint32_t)min(max(v, 0), 255);
+__device__ __forceinline__ uint32_t clip8_q22(int v) {  // Pillow clip8: (v >> 22) clamped to 0..255
+  uint32_t r;
+  asm("cvt.sat.u8.s32 %0, %1;" : "=r"(r) : "r"(v >> 22));
+  return r;
+}
+__device__ __forceinline__ int lds_s32(uint32_t addr) {
+  int v;
+  // volatile: must not be scheduled across the barriers that publish the tables it reads
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
 }
 
 // merges [xs, xe] into a small unsorted list of disjoint, non-adjacent spans
@@ -152,10 +164,9 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, uint8_t *__restri
   const int SEGCAP = L.segcap;
   const int M = rd.max_spans;
   int32_t *s_prefix = reinterpret_cast<int32_t *>(smem + L.off_prefix);
-  int32_t *s_prog = reinterpret_cast<int32_t *>(smem + L.off_prog);
   uint32_t *s_xwin = reinterpret_cast<uint32_t *>(smem + L.off_xwin);
   uint32_t *s_ywin = reinterpret_cast<uint32_t *>(smem + L.off_ywin);
-  uint2 *s_ht = reinterpret_cast<uint2 *>(smem + L.off_scratch);
+  uint32_t *s_ht = reinterpret_cast<uint32_t *>(smem + L.off_scratch);
   uint8_t *s_frame = smem + L.off_frame;
   // phase-B view of the scratch area: per-row crossing lists
   const int CAP = L.cap;
@@ -178,9 +189,12 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, uint8_t *__restri
     s_nv[tid] = shape ? st.shape_n[shape] : 0;
     const uint32_t col = st.p_rgb[scene];
     s_rgb[tid] = (int)col;
-    s_dr[tid] = (int)(col & 255u) - (int)(rd.bg & 255u);
-    s_dg[tid] = (int)((col >> 8) & 255u) - (int)((rd.bg >> 8) & 255u);
-    s_db[tid] = (int)((col >> 16) & 255u) - (int)((rd.bg >> 16) & 255u);
+    {  // colour - background per channel, three signed 10-bit fields
+      const int dr = (int)(col & 255u) - (int)(rd.bg & 255u);
+      const int dg = (int)((col >> 8) & 255u) - (int)((rd.bg >> 8) & 255u);
+      const int db = (int)((col >> 16) & 255u) - (int)((rd.bg >> 16) & 255u);
+      s_dr[tid] = (dr & 1023) | ((dg & 1023) << 10) | ((db & 1023) << 20);
+    }
     s_px[tid] = st.pos_x[e * S + tid];
     s_py[tid] = st.pos_y[e * S + tid];
     s_m[0 * S + tid] = st.p_m00[scene];
@@ -190,7 +204,6 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, uint8_t *__restri
     s_nh[tid] = 0;
   }
   for (int i = tid; i < rd.ncls_x * 33; i += R_THREADS) s_prefix[i] = rd.ax.prefix[i];
-  for (int i = tid; i < rd.ncls_y * PROG_STRIDE; i += R_THREADS) s_prog[i] = rd.ay.program[i];
   for (int i = tid; i < n_rows; i += R_THREADS) s_nseg[i] = 0;
   for (int i = tid; i < rd.W; i += R_THREADS)
     s_xwin[i] = (uint32_t)(uint16_t)rd.ax.win_min[i] | ((uint32_t)rd.ax.win_len[i] << 16) |
@@ -526,7 +539,7 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, uint8_t *__restri
   // A region of h x w outputs is cut into ceil(h/32) row blocks and, per row block, into as
   // few equal column blocks as fit HT_ITEMS H values (columns need no halo, rows do).
   const int bg_r = rd.bg & 255u, bg_g = (rd.bg >> 8) & 255u, bg_b = (rd.bg >> 16) & 255u;
-  const uint2 bg_h = make_uint2((uint32_t)bg_r | ((uint32_t)bg_g << 16), (uint32_t)bg_b);
+  const uint32_t bg_h = (uint32_t)bg_r | ((uint32_t)bg_g << 10) | ((uint32_t)bg_b << 20);
   for (int s = 0; s < S; ++s) {
     const int ryo0 = s_region[s * 4 + 0], ryo1 = s_region[s * 4 + 1];
     const int rxo0 = s_region[s * 4 + 2], rxo1 = s_region[s * 4 + 3];
@@ -554,24 +567,28 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, uint8_t *__restri
             const int ktot = P[len];
             const int base_r = bg_r * ktot + (1 << 21), base_g = bg_g * ktot + (1 << 21),
                       base_b = bg_b * ktot + (1 << 21);
+            const uint32_t p_addr = (uint32_t)__cvta_generic_to_shared(P);
+            const uint32_t seg_addr0 = (uint32_t)__cvta_generic_to_shared(s_segs);
+            const uint32_t dcol_addr = (uint32_t)__cvta_generic_to_shared(s_dr);
             for (int r = rgroup; r < nr; r += rstride) {
               const int ry = tr0 + r - row_b0;
               const int nseg = s_nseg[ry];
-              uint2 hval = bg_h;
+              uint32_t hval = bg_h;
               if (nseg) {
-                const uint32_t *seg = s_segs + (size_t)ry * SEGCAP;
+                uint32_t seg_addr = seg_addr0 + (uint32_t)(ry * SEGCAP) * 4u;
                 int ar = base_r, ag = base_g, ab = base_b;
-                for (int j = 0; j < nseg; ++j) {
-                  const uint32_t w = seg[j];
+#pragma unroll 1
+                for (int j = 0; j < nseg; ++j, seg_addr += 4u) {
+                  const uint32_t w = (uint32_t)lds_s32(seg_addr);
                   const int a = min(max((int)(w & 0xFFFu) - xmin, 0), len);
                   const int b = min(max((int)((w >> 12) & 0xFFFu) + 1 - xmin, 0), len);
-                  const int wt = P[b] - P[a];
-                  const int sp = (int)(w >> 24);
-                  ar += s_dr[sp] * wt;
-                  ag += s_dg[sp] * wt;
-                  ab += s_db[sp] * wt;
+                  const int wt = lds_s32(p_addr + ((uint32_t)b << 2)) - lds_s32(p_addr + ((uint32_t)a << 2));
+                  const int d = lds_s32(dcol_addr + ((w >> 24) << 2));
+                  ar += ((d << 22) >> 22) * wt;
+                  ag += ((d << 12) >> 22) * wt;
+                  ab += ((d << 2) >> 22) * wt;
                 }
-                hval = make_uint2(clip8_q22(ar) | (clip8_q22(ag) << 16), clip8_q22(ab));
+                hval = clip8_q22(ar) | (clip8_q22(ag) << 10) | (clip8_q22(ab) << 20);
               }
               s_ht[r * TILE_X_MAX + c] = hval;
             }
@@ -585,47 +602,45 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, uint8_t *__restri
           const int yo = ty0 + ly;
           const uint32_t yw = s_ywin[yo - yo_b0];
           const int rbase = (int)(int16_t)(yw & 0xFFFFu) - tr0;
-          const int32_t *prog = s_prog + (int)(yw >> 24) * PROG_STRIDE;
-          const int np = prog[0], ns = prog[1] & 0xFFFF;
+          const int cls = (int)(yw >> 24);
           int ar = 1 << 21, ag = 1 << 21, ab = 1 << 21;
-          const int2 *pp = reinterpret_cast<const int2 *>(prog + 2);
-          const int2 *ps = reinterpret_cast<const int2 *>(prog + 2 + 2 * 16);
-          const uint2 *col_ht = s_ht + rbase * TILE_X_MAX + c;
-          if (prog[1] >> 16) {
+          const uint32_t *col_ht = s_ht + rbase * TILE_X_MAX + c;
+          if (cls == rd.a5_cls) {
             // interior rows of a 5x reduction: taps (k, 28-k) pair up, 4/9/19/24/29 are zero,
-            // 14 is the centre -> every load has an immediate offset
+            // 14 is the centre -> immediate load offsets, coefficients from the constant bank
             constexpr int A5[12] = {0, 1, 2, 3, 5, 6, 7, 8, 10, 11, 12, 13};
 #pragma unroll
             for (int k = 0; k < 12; ++k) {
-              const int kk = pp[k].y;
-              const uint2 u = col_ht[A5[k] * TILE_X_MAX];
-              const uint2 v = col_ht[(28 - A5[k]) * TILE_X_MAX];
-              const uint32_t rg = u.x + v.x, bb = u.y + v.y;
-              ar += (int)(rg & 0xFFFFu) * kk;
-              ag += (int)(rg >> 16) * kk;
-              ab += (int)bb * kk;
+              const int kk = rd.a5_coef[k];
+              // two taps of equal coefficient: the 10-bit fields hold sums up to 510
+              const uint32_t t = col_ht[A5[k] * TILE_X_MAX] + col_ht[(28 - A5[k]) * TILE_X_MAX];
+              ar += (int)(t & 1023u) * kk;
+              ag += (int)((t >> 10) & 1023u) * kk;
+              ab += (int)(t >> 20) * kk;
             }
-            const int kk = ps[0].y;
-            const uint2 u = col_ht[14 * TILE_X_MAX];
-            ar += (int)(u.x & 0xFFFFu) * kk;
-            ag += (int)(u.x >> 16) * kk;
-            ab += (int)u.y * kk;
+            const int kk = rd.a5_coef[12];
+            const uint32_t t = col_ht[14 * TILE_X_MAX];
+            ar += (int)(t & 1023u) * kk;
+            ag += (int)((t >> 10) & 1023u) * kk;
+            ab += (int)(t >> 20) * kk;
           } else {
+            const int32_t *prog = rd.ay.program + cls * PROG_STRIDE;  // global, read-only
+            const int np = __ldg(prog), ns = __ldg(prog + 1) & 0xFFFF;
+            const int2 *pp = reinterpret_cast<const int2 *>(prog + 2);
+            const int2 *ps = reinterpret_cast<const int2 *>(prog + 2 + 2 * 16);
             for (int k = 0; k < np; ++k) {
-              const int2 pk = pp[k];  // (row a | row b << 8, coefficient)
-              const uint2 u = col_ht[(pk.x & 255) * TILE_X_MAX];
-              const uint2 v = col_ht[(pk.x >> 8) * TILE_X_MAX];
-              const uint32_t rg = u.x + v.x, bb = u.y + v.y;
-              ar += (int)(rg & 0xFFFFu) * pk.y;
-              ag += (int)(rg >> 16) * pk.y;
-              ab += (int)bb * pk.y;
+              const int2 pk = __ldg(pp + k);  // (row a | row b << 8, coefficient)
+              const uint32_t t = col_ht[(pk.x & 255) * TILE_X_MAX] + col_ht[(pk.x >> 8) * TILE_X_MAX];
+              ar += (int)(t & 1023u) * pk.y;
+              ag += (int)((t >> 10) & 1023u) * pk.y;
+              ab += (int)(t >> 20) * pk.y;
             }
             for (int k = 0; k < ns; ++k) {
-              const int2 pk = ps[k];
-              const uint2 u = col_ht[pk.x * TILE_X_MAX];
-              ar += (int)(u.x & 0xFFFFu) * pk.y;
-              ag += (int)(u.x >> 16) * pk.y;
-              ab += (int)u.y * pk.y;
+              const int2 pk = __ldg(ps + k);
+              const uint32_t t = col_ht[pk.x * TILE_X_MAX];
+              ar += (int)(t & 1023u) * pk.y;
+              ag += (int)((t >> 10) & 1023u) * pk.y;
+              ab += (int)(t >> 20) * pk.y;
             }
           }
           uint8_t *px = s_frame + ((size_t)(yo - yo_b0) * rd.W + tx0 + c) * 3;
