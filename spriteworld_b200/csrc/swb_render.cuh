@@ -44,7 +44,7 @@ constexpr int EV = SWB_MAX_VERTS;  // edge slots per sprite
 struct RenderLayout {
   int S, rows, M, band_rows, W, aa, ncx, ncy, cap;
   int off_pos, off_meta, off_iv, off_edge_i, off_edge_f, off_edge_b, off_edge_yr, off_hl, off_region;
-  int off_nseg, off_segs, off_prefix, off_xwin, off_ywin, off_scratch, off_frame, total;
+  int off_nseg, off_segs, off_prefix, off_xwin, off_ywin, off_scratch, off_frame, off_join, total;
   int scratch_bytes, list_rows, segcap;
   __host__ __device__ RenderLayout(int S_, int rows_, int M_, int band_rows_, int W_, int aa_,
                                    int ncx_, int ncy_)
@@ -53,14 +53,14 @@ struct RenderLayout {
     auto take = [&](int bytes) { int r = o; o += (bytes + 15) & ~15; return r; };
     off_pos = take(S * 6 * 8);
     off_meta = take(S * 20 * 4);
-    off_iv = take(S * EV * 2 * 4);
     off_edge_i = take(S * EV * 4 * 4);     // x0, y0, ymin, ymax
-    off_edge_f = take(S * EV * 7 * 4);     // dx, ovs, ove, join nv (start/end), join owner (start/end)
+    off_edge_f = take(S * EV * 3 * 4);     // dx, ovs (override on the first row), ove (on the last row)
     off_edge_b = take(S * EV * 3);         // flag, join partner (start), join partner (end)
     off_edge_yr = take(S * EV * 4);        // ymin | ymax<<16 of non-horizontal edges, empty otherwise
     off_hl = take(S * EV * 3 * 2);         // horizontal edges: y, xmin, xmax (int16)
     off_region = take(S * 4 * 2);
-    segcap = (M > 1 || S > 8) ? 16 : 8;    // visible segments kept per canvas row
+    // visible segments kept per canvas row: n one-span sprites leave at most 2n-1 pieces
+    segcap = M > 1 ? 16 : (2 * S < 4 ? 4 : (2 * S > 16 ? 16 : 2 * S));
     off_nseg = take(rows);
     off_segs = take(rows * segcap * 4);
     off_prefix = take(ncx * 33 * 4);
@@ -76,8 +76,13 @@ struct RenderLayout {
     if (ht_bytes + ((frame_bytes + 15) & ~15) < need_b) ht_bytes = need_b - frame_bytes;
     off_scratch = take(ht_bytes);
     off_frame = take(frame_bytes);
+    scratch_bytes = o - off_scratch;
+    // phase-A temporaries (integer vertices, corner-join candidates) live in the scratch area
+    // when they fit, else behind it
+    const int a_bytes = S * EV * 6 * 4;
+    off_iv = a_bytes <= scratch_bytes ? off_scratch : take(a_bytes);
+    off_join = off_iv + S * EV * 2 * 4;
     total = o;
-    scratch_bytes = total - off_scratch;
     list_rows = scratch_bytes / (cap * 4 + 4);  // upper bound; phase B sizes its chunks itself
   }
 };
@@ -95,6 +100,14 @@ __device__ __forceinline__ uint32_t clip8_q22(int v) {  // Pillow clip8: (v >> 2
   uint32_t r;
   asm("cvt.sat.u8.s32 %0, %1;" : "=r"(r) : "r"(v >> 22));
   return r;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" : : "r"(addr), "r"(v) : "memory");
 }
 __device__ __forceinline__ int lds_s32(uint32_t addr) {
   int v;
@@ -151,7 +164,7 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, uint8_t *__restri
   int *e_y0 = e_x0 + S * EV, *e_ymin = e_y0 + S * EV, *e_ymax = e_ymin + S * EV;
   float *e_dx = reinterpret_cast<float *>(smem + L.off_edge_f);
   float *e_ovs = e_dx + S * EV, *e_ove = e_ovs + S * EV;
-  float *e_jvs = e_ove + S * EV, *e_jve = e_jvs + S * EV;
+  float *e_jvs = reinterpret_cast<float *>(smem + L.off_join), *e_jve = e_jvs + S * EV;
   int *e_own_s = reinterpret_cast<int *>(e_jve + S * EV), *e_own_e = e_own_s + S * EV;  // latest joiner of k
   uint8_t *e_flag = smem + L.off_edge_b;
   int8_t *e_jks = reinterpret_cast<int8_t *>(e_flag + S * EV);
@@ -554,43 +567,64 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, uint8_t *__restri
       for (int tx0 = rxo0; tx0 <= rxo1; tx0 += nx_blk) {
         const int nx = min(nx_blk, rxo1 - tx0 + 1);
         const uint32_t inv_nx = nx == nx_blk ? (uint32_t)s_pinv[s] : (1u << 20) / (uint32_t)nx + 1u;
-        // ---- H pass: a thread keeps its column c and strides over the canvas rows, so the
-        // window start/length, tap prefix table and bg*K are loop invariants ----
+        // ---- H pass: a thread owns two columns (c, c + half) and strides over the canvas
+        // rows, so the window start/length, tap prefix table and bg*K are loop invariants and
+        // the row's segment records are decoded once for both columns ----
         {
-          const int rgroup = (int)(((uint32_t)tid * inv_nx) >> 20);  // tid / nx
-          const int c = tid - rgroup * nx;
-          const int rstride = R_THREADS / nx;                       // row groups per pass
+          const int half = (nx + 1) >> 1;
+          const uint32_t inv_half = (1u << 20) / (uint32_t)half + 1u;
+          const int rgroup = (int)(((uint32_t)tid * inv_half) >> 20);  // tid / half
+          const int c0 = tid - rgroup * half, c1 = c0 + half;
+          const int rstride = (int)(((uint32_t)R_THREADS * inv_half) >> 20);  // row groups per pass
           if (rgroup < rstride) {
-            const uint32_t xw = s_xwin[tx0 + c];
-            const int xmin = (int)(int16_t)(xw & 0xFFFFu), len = (int)((xw >> 16) & 0xFFu);
-            const int32_t *P = s_prefix + (int)(xw >> 24) * 33;
-            const int ktot = P[len];
-            const int base_r = bg_r * ktot + (1 << 21), base_g = bg_g * ktot + (1 << 21),
-                      base_b = bg_b * ktot + (1 << 21);
-            const uint32_t p_addr = (uint32_t)__cvta_generic_to_shared(P);
-            const uint32_t seg_addr0 = (uint32_t)__cvta_generic_to_shared(s_segs);
+            const bool two = c1 < nx;
+            const uint32_t xw0 = s_xwin[tx0 + c0], xw1 = s_xwin[tx0 + (two ? c1 : c0)];
+            const int xmin0 = (int)(int16_t)(xw0 & 0xFFFFu), len0 = (int)((xw0 >> 16) & 0xFFu);
+            const int xmin1 = (int)(int16_t)(xw1 & 0xFFFFu), len1 = (int)((xw1 >> 16) & 0xFFu);
+            const uint32_t prefix0 = (uint32_t)__cvta_generic_to_shared(s_prefix);
+            const uint32_t p0 = prefix0 + (xw0 >> 24) * 33u * 4u, p1 = prefix0 + (xw1 >> 24) * 33u * 4u;
+            const int k0 = lds_s32(p0 + ((uint32_t)len0 << 2)), k1 = lds_s32(p1 + ((uint32_t)len1 << 2));
+            const int b0r = bg_r * k0 + (1 << 21), b0g = bg_g * k0 + (1 << 21), b0b = bg_b * k0 + (1 << 21);
+            const int b1r = bg_r * k1 + (1 << 21), b1g = bg_g * k1 + (1 << 21), b1b = bg_b * k1 + (1 << 21);
             const uint32_t dcol_addr = (uint32_t)__cvta_generic_to_shared(s_dr);
-            for (int r = rgroup; r < nr; r += rstride) {
-              const int ry = tr0 + r - row_b0;
-              const int nseg = s_nseg[ry];
-              uint32_t hval = bg_h;
+            // raw shared-window addresses, advanced by one row group per iteration
+            uint32_t nseg_addr = (uint32_t)__cvta_generic_to_shared(s_nseg) + (uint32_t)(tr0 + rgroup - row_b0);
+            uint32_t seg_row = (uint32_t)__cvta_generic_to_shared(s_segs) +
+                               (uint32_t)((tr0 + rgroup - row_b0) * SEGCAP) * 4u;
+            uint32_t ht_addr = (uint32_t)__cvta_generic_to_shared(s_ht) + (uint32_t)(rgroup * TILE_X_MAX + c0) * 4u;
+            const uint32_t seg_step = (uint32_t)(rstride * SEGCAP) * 4u;
+            const uint32_t ht_step = (uint32_t)(rstride * TILE_X_MAX) * 4u;
+            const uint32_t ht_second = (uint32_t)half * 4u;
+            for (int r = rgroup; r < nr; r += rstride, nseg_addr += rstride, seg_row += seg_step, ht_addr += ht_step) {
+              const int nseg = (int)lds_u8(nseg_addr);
+              uint32_t h0 = bg_h, h1 = bg_h;
               if (nseg) {
-                uint32_t seg_addr = seg_addr0 + (uint32_t)(ry * SEGCAP) * 4u;
-                int ar = base_r, ag = base_g, ab = base_b;
+                uint32_t seg_addr = seg_row;
+                int r0 = b0r, g0 = b0g, bl0 = b0b, r1 = b1r, g1 = b1g, bl1 = b1b;
+                int j = nseg;
 #pragma unroll 1
-                for (int j = 0; j < nseg; ++j, seg_addr += 4u) {
+                do {
                   const uint32_t w = (uint32_t)lds_s32(seg_addr);
-                  const int a = min(max((int)(w & 0xFFFu) - xmin, 0), len);
-                  const int b = min(max((int)((w >> 12) & 0xFFFu) + 1 - xmin, 0), len);
-                  const int wt = lds_s32(p_addr + ((uint32_t)b << 2)) - lds_s32(p_addr + ((uint32_t)a << 2));
+                  seg_addr += 4u;
+                  const int xs = (int)(w & 0xFFFu), xe1 = (int)((w >> 12) & 0xFFFu) + 1;
                   const int d = lds_s32(dcol_addr + ((w >> 24) << 2));
-                  ar += ((d << 22) >> 22) * wt;
-                  ag += ((d << 12) >> 22) * wt;
-                  ab += ((d << 2) >> 22) * wt;
-                }
-                hval = clip8_q22(ar) | (clip8_q22(ag) << 10) | (clip8_q22(ab) << 20);
+                  const int dr = (d << 22) >> 22, dg = (d << 12) >> 22, db = (d << 2) >> 22;
+                  {
+                    const int a = min(max(xs - xmin0, 0), len0), b = min(max(xe1 - xmin0, 0), len0);
+                    const int wt = lds_s32(p0 + ((uint32_t)b << 2)) - lds_s32(p0 + ((uint32_t)a << 2));
+                    r0 += dr * wt; g0 += dg * wt; bl0 += db * wt;
+                  }
+                  {
+                    const int a = min(max(xs - xmin1, 0), len1), b = min(max(xe1 - xmin1, 0), len1);
+                    const int wt = lds_s32(p1 + ((uint32_t)b << 2)) - lds_s32(p1 + ((uint32_t)a << 2));
+                    r1 += dr * wt; g1 += dg * wt; bl1 += db * wt;
+                  }
+                } while (--j);
+                h0 = clip8_q22(r0) | (clip8_q22(g0) << 10) | (clip8_q22(bl0) << 20);
+                h1 = clip8_q22(r1) | (clip8_q22(g1) << 10) | (clip8_q22(bl1) << 20);
               }
-              s_ht[r * TILE_X_MAX + c] = hval;
+              sts_u32(ht_addr, h0);
+              if (two) sts_u32(ht_addr + ht_second, h1);
             }
           }
         }
