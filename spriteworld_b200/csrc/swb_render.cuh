@@ -52,7 +52,7 @@ struct RenderLayout {
     int o = 0;
     auto take = [&](int bytes) { int r = o; o += (bytes + 15) & ~15; return r; };
     off_pos = take(S * 6 * 8);
-    off_meta = take(S * 20 * 4);
+    off_meta = take(S * 22 * 4);
     off_edge_i = take(S * EV * 4 * 4);     // x0, y0, ymin, ymax
     off_edge_f = take(S * EV * 3 * 4);     // dx, ovs (override on the first row), ove (on the last row)
     off_edge_b = take(S * EV * 3);         // flag, join partner (start), join partner (end)
@@ -158,6 +158,7 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, uint8_t *__restri
   int *s_r0 = s_shape + S, *s_rcnt = s_r0 + S, *s_nh = s_rcnt + S, *s_roff = s_nh + S;
   int *s_dr = s_roff + S, *s_dg = s_dr + S, *s_db = s_dg + S;       // colour - background
   int *s_pny = s_db + S, *s_pnx = s_pny + S, *s_pinv = s_pnx + S;  // tile plan of the region
+  int *s_pinvh = s_pinv + S, *s_hasov = s_pinvh + S;  // any corner-join override on this sprite
   int *s_ivx = reinterpret_cast<int *>(smem + L.off_iv);
   int *s_ivy = s_ivx + S * EV;
   int *e_x0 = reinterpret_cast<int *>(smem + L.off_edge_i);
@@ -215,6 +216,7 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, uint8_t *__restri
     s_m[2 * S + tid] = st.p_m10[scene];
     s_m[3 * S + tid] = st.p_m11[scene];
     s_nh[tid] = 0;
+    s_hasov[tid] = 0;
   }
   for (int i = tid; i < rd.ncls_x * 33; i += R_THREADS) s_prefix[i] = rd.ax.prefix[i];
   for (int i = tid; i < n_rows; i += R_THREADS) s_nseg[i] = 0;
@@ -329,6 +331,7 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, uint8_t *__restri
     }
     s_pny[tid] = pny; s_pnx[tid] = pnx;
     s_pinv[tid] = (int)((1u << 20) / (uint32_t)pnx + 1u);  // it / pnx == (it * inv) >> 20 for it < 2^20 / pnx
+    s_pinvh[tid] = (int)((1u << 20) / (uint32_t)((pnx + 1) >> 1) + 1u);
   }
   __syncthreads();
 
@@ -375,8 +378,8 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, uint8_t *__restri
   for (int t = tid; t < S * EV; t += R_THREADS) {
     const int i = t % EV, base = t - i;
     const int ks = e_jks[t], ke = e_jke[t];
-    if (ks >= 0 && e_own_s[base + ks] == i) e_ovs[base + ks] = e_jvs[t];
-    if (ke >= 0 && e_own_e[base + ke] == i) e_ove[base + ke] = e_jve[t];
+    if (ks >= 0 && e_own_s[base + ks] == i) { e_ovs[base + ks] = e_jvs[t]; s_hasov[t / EV] = 1; }
+    if (ke >= 0 && e_own_e[base + ke] == i) { e_ove[base + ke] = e_jve[t]; s_hasov[t / EV] = 1; }
   }
   __syncthreads();
 
@@ -409,6 +412,7 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, uint8_t *__restri
       while (rem >= s_rcnt[s]) { rem -= s_rcnt[s]; ++s; }
       const int y = s_r0[s] + rem;
       const int base = s * EV, ne = s_nv[s], p_ymax = s_pymax[s];
+      const bool hasov = s_hasov[s] != 0;
       float *xx = reinterpret_cast<float *>(smem + L.off_scratch) + (size_t)t * CAP;
       int j = 0;
       bool ovf = false;
@@ -418,8 +422,10 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, uint8_t *__restri
         if (y < ymin || y > ymax) continue;
         const int u = base + i;
         float x = edge_x_at(y, e_y0[u], e_dx[u], e_x0[u]);
-        if (y == ymin) { const float o = e_ovs[u]; if (!isnan(o)) x = o; }
-        if (y == p_ymax && y == ymax) { const float o = e_ove[u]; if (!isnan(o)) x = o; }
+        if (hasov) {  // corner-join overrides (rare: acute same-direction corners only)
+          if (y == ymin) { const float o = e_ovs[u]; if (!isnan(o)) x = o; }
+          if (y == p_ymax && y == ymax) { const float o = e_ove[u]; if (!isnan(o)) x = o; }
+        }
         const int twice = (y == ymax && y < p_ymax) ? 2 : 1;  // edge ending on an interior row
         if (j + twice <= CAP) {
           xx[j] = x;
@@ -572,7 +578,7 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, uint8_t *__restri
         // the row's segment records are decoded once for both columns ----
         {
           const int half = (nx + 1) >> 1;
-          const uint32_t inv_half = (1u << 20) / (uint32_t)half + 1u;
+          const uint32_t inv_half = nx == nx_blk ? (uint32_t)s_pinvh[s] : (1u << 20) / (uint32_t)half + 1u;
           const int rgroup = (int)(((uint32_t)tid * inv_half) >> 20);  // tid / half
           const int c0 = tid - rgroup * half, c1 = c0 + half;
           const int rstride = (int)(((uint32_t)R_THREADS * inv_half) >> 20);  // row groups per pass
@@ -692,8 +698,11 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, uint8_t *__restri
   const int row_bytes = rd.W * 3;
   if ((row_bytes & 15) == 0) {
     const int vec_per_row = row_bytes >> 4;
+    const uint32_t inv_vpr = (1u << 20) / (uint32_t)vec_per_row + 1u;  // i / vec_per_row for i < 2^20 / vpr
+    const bool fast = n_yo * vec_per_row < (1 << 20) / vec_per_row;
     for (int i = tid; i < n_yo * vec_per_row; i += R_THREADS) {
-      const int ly = i / vec_per_row, v = i - ly * vec_per_row;
+      const int ly = fast ? (int)(((uint32_t)i * inv_vpr) >> 20) : i / vec_per_row;
+      const int v = i - ly * vec_per_row;
       const uint4 val = reinterpret_cast<const uint4 *>(s_frame + (size_t)ly * row_bytes)[v];
       const int out_row = rd.H - 1 - (yo_b0 + ly);
       reinterpret_cast<uint4 *>(dst_frame + (size_t)out_row * row_bytes)[v] = val;

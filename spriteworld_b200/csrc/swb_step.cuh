@@ -379,6 +379,7 @@ step_kernel(DevState st, const void *__restrict__ actions, int action_dtype, swb
             const double tx = offset_component(ws.x[body], ws.f32[body], ws.x[s], ws.f32[s]);
             const double ty = offset_component(ws.y[body], ws.f32[body], ws.y[s], ws.f32[s]);
             if (warp_contains(st, ws, s, tx, ty, lane)) {
+              __syncwarp();  // every lane is done reading the pose lane 0 overwrites
               if (lane == 0) sprite_move(ws, s, mx, my, keep);
               break;
             }
@@ -420,6 +421,7 @@ step_kernel(DevState st, const void *__restrict__ actions, int action_dtype, swb
         const double tx = offset_component(px, af32, ws.x[s], ws.f32[s]);
         const double ty = offset_component(py, af32, ws.y[s], ws.f32[s]);
         if (warp_contains(st, ws, s, tx, ty, lane)) {
+          __syncwarp();
           if (lane == 0) sprite_move(ws, s, mx, my, keep);
           break;
         }
