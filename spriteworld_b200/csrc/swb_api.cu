@@ -560,6 +560,15 @@ int swb_upload_state(swb_engine *eng, const double *pos_x, const double *pos_y, 
   return 0;
 }
 
+#ifdef SWB_PHASE_CLOCKS
+// debug build only: cumulative cycles per render phase (see SWB_MARK); resets the counters
+int swb_debug_phase_clocks(unsigned long long *out16) {
+  unsigned long long zero[16] = {0};
+  if (cudaMemcpyFromSymbol(out16, swb::g_phase_clk, sizeof(zero)) != cudaSuccess) return 1;
+  return cudaMemcpyToSymbol(swb::g_phase_clk, zero, sizeof(zero)) != cudaSuccess;
+}
+#endif
+
 int64_t swb_launch_count(const swb_engine *eng) { return eng ? eng->launches : 0; }
 
 }  // extern "C"

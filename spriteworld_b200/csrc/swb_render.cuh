@@ -40,22 +40,21 @@ constexpr int HT_ROWS = 112;      // canvas rows a tile's H buffer holds
 constexpr int HT_ITEMS = HT_ROWS * TILE_X_MAX;
 constexpr int MAX_ROW_SPANS = 12;
 constexpr int EV = SWB_MAX_VERTS;  // edge slots per sprite
+static_assert(EV == 32, "phase A maps one lane to one vertex / edge");
 
 struct RenderLayout {
   int S, rows, M, band_rows, W, aa, ncx, ncy, cap;
-  int off_pos, off_meta, off_iv, off_edge_i, off_edge_f, off_edge_b, off_edge_yr, off_hl, off_region;
-  int off_nseg, off_segs, off_prefix, off_xwin, off_ywin, off_scratch, off_frame, off_join, total;
+  int off_meta, off_edge_i, off_edge_f, off_edge_yr, off_hl, off_region;
+  int off_nseg, off_segs, off_prefix, off_xwin, off_ywin, off_scratch, off_frame, total;
   int scratch_bytes, list_rows, segcap;
   __host__ __device__ RenderLayout(int S_, int rows_, int M_, int band_rows_, int W_, int aa_,
                                    int ncx_, int ncy_)
       : S(S_), rows(rows_), M(M_), band_rows(band_rows_), W(W_), aa(aa_), ncx(ncx_), ncy(ncy_) {
     int o = 0;
     auto take = [&](int bytes) { int r = o; o += (bytes + 15) & ~15; return r; };
-    off_pos = take(S * 6 * 8);
-    off_meta = take(S * 22 * 4);
-    off_edge_i = take(S * EV * 4 * 4);     // x0, y0, ymin, ymax
+    off_meta = take(S * (12 + 8) * 4);     // 12 plan ints + 8 active-edge masks per sprite
+    off_edge_i = take(S * EV * 2 * 4);     // x0, y0
     off_edge_f = take(S * EV * 3 * 4);     // dx, ovs (override on the first row), ove (on the last row)
-    off_edge_b = take(S * EV * 3);         // flag, join partner (start), join partner (end)
     off_edge_yr = take(S * EV * 4);        // ymin | ymax<<16 of non-horizontal edges, empty otherwise
     off_hl = take(S * EV * 3 * 2);         // horizontal edges: y, xmin, xmax (int16)
     off_region = take(S * 4 * 2);
@@ -77,11 +76,6 @@ struct RenderLayout {
     off_scratch = take(ht_bytes);
     off_frame = take(frame_bytes);
     scratch_bytes = o - off_scratch;
-    // phase-A temporaries (integer vertices, corner-join candidates) live in the scratch area
-    // when they fit, else behind it
-    const int a_bytes = S * EV * 6 * 4;
-    off_iv = a_bytes <= scratch_bytes ? off_scratch : take(a_bytes);
-    off_join = off_iv + S * EV * 2 * 4;
     total = o;
     list_rows = scratch_bytes / (cap * 4 + 4);  // upper bound; phase B sizes its chunks itself
   }
@@ -139,6 +133,22 @@ __device__ __forceinline__ void add_span(int *lxs, int *lxe, int &n, int xs, int
   }
 }
 
+// Debug-only phase timers (nvcc -DSWB_PHASE_CLOCKS): thread 0 of every CTA adds the cycles
+// between consecutive marks to g_phase_clk[id].  Not part of the shipped library.
+#ifdef SWB_PHASE_CLOCKS
+__device__ unsigned long long g_phase_clk[16];
+#define SWB_MARK(id)                                                              \
+  do {                                                                            \
+    if (tid == 0) {                                                               \
+      const long long now_ = clock64();                                           \
+      atomicAdd(&g_phase_clk[id], (unsigned long long)(now_ - mark_));            \
+      mark_ = now_;                                                               \
+    }                                                                             \
+  } while (0)
+#else
+#define SWB_MARK(id) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(R_THREADS)
 render_kernel(DevState st, RasterDev rd, const RenderLayout L, uint8_t *__restrict__ frames,
               int env_base) {
@@ -148,28 +158,20 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, uint8_t *__restri
   const int tid = threadIdx.x;
   const int S = st.S;
 
-  double *s_px = reinterpret_cast<double *>(smem + L.off_pos);
-  double *s_py = s_px + S;
-  double *s_m = s_py + S;  // [4][S]
+  // per-sprite plan (ints): vertex count, last polygon row, first row / row count in this
+  // band, horizontal-edge count, bucket shift of the active-edge masks, colour - background,
+  // tile plan of the region, "has a corner join"
   int *s_nv = reinterpret_cast<int *>(smem + L.off_meta);
-  int *s_rgb = s_nv + S;
-  int *s_xmin = s_rgb + S, *s_xmax = s_xmin + S, *s_gymin = s_xmax + S, *s_gymax = s_gymin + S;
-  int *s_pymin = s_gymax + S, *s_pymax = s_pymin + S, *s_shape = s_pymax + S;
-  int *s_r0 = s_shape + S, *s_rcnt = s_r0 + S, *s_nh = s_rcnt + S, *s_roff = s_nh + S;
-  int *s_dr = s_roff + S, *s_dg = s_dr + S, *s_db = s_dg + S;       // colour - background
-  int *s_pny = s_db + S, *s_pnx = s_pny + S, *s_pinv = s_pnx + S;  // tile plan of the region
-  int *s_pinvh = s_pinv + S, *s_hasov = s_pinvh + S;  // any corner-join override on this sprite
-  int *s_ivx = reinterpret_cast<int *>(smem + L.off_iv);
-  int *s_ivy = s_ivx + S * EV;
+  int *s_pymax = s_nv + S, *s_r0 = s_pymax + S, *s_rcnt = s_r0 + S, *s_nh = s_rcnt + S;
+  int *s_bsh = s_nh + S, *s_dr = s_bsh + S;
+  int *s_pny = s_dr + S, *s_pnx = s_pny + S, *s_pinv = s_pnx + S;
+  int *s_pinvh = s_pinv + S, *s_hasov = s_pinvh + S;
+  unsigned *s_emask = reinterpret_cast<unsigned *>(s_hasov + S);  // [S][8] active edges per row bucket
+  // edge table: start vertex, slope, corner-join overrides on the first / last row
   int *e_x0 = reinterpret_cast<int *>(smem + L.off_edge_i);
-  int *e_y0 = e_x0 + S * EV, *e_ymin = e_y0 + S * EV, *e_ymax = e_ymin + S * EV;
+  int *e_y0 = e_x0 + S * EV;
   float *e_dx = reinterpret_cast<float *>(smem + L.off_edge_f);
   float *e_ovs = e_dx + S * EV, *e_ove = e_ovs + S * EV;
-  float *e_jvs = reinterpret_cast<float *>(smem + L.off_join), *e_jve = e_jvs + S * EV;
-  int *e_own_s = reinterpret_cast<int *>(e_jve + S * EV), *e_own_e = e_own_s + S * EV;  // latest joiner of k
-  uint8_t *e_flag = smem + L.off_edge_b;
-  int8_t *e_jks = reinterpret_cast<int8_t *>(e_flag + S * EV);
-  int8_t *e_jke = e_jks + S * EV;
   uint32_t *e_yr = reinterpret_cast<uint32_t *>(smem + L.off_edge_yr);
   short *s_hl = reinterpret_cast<short *>(smem + L.off_hl);  // [S][EV][3]
   short *s_region = reinterpret_cast<short *>(smem + L.off_region);  // [S][4] yo0,yo1,xo0,xo1
@@ -194,30 +196,21 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, uint8_t *__restri
   const int row_b1 = rd.ay.win_min[yo_b1 - 1] + rd.ay.win_len[yo_b1 - 1];  // exclusive
   const int n_rows = row_b1 - row_b0;
 
-  // ---- phase 0: sprite records of this env's current scene, tables -------------------
+#ifdef SWB_PHASE_CLOCKS
+  long long mark_ = clock64();
+#endif
+  // ---- phase A: a warp per sprite, a lane per vertex / edge ------------------------------
+  // Everything Pillow derives from the vertex list before it scans rows: integer vertices,
+  // the edge table (add_edge), horizontal edges, extents, the corner joins -- plus this
+  // kernel's own per-sprite plan (rows, output region, tiles, active-edge masks).  Neighbour
+  // vertices come by shuffle, extents by warp reductions, "edges that share a start row" by
+  // match_any; nothing leaves the warp until the barrier that ends the phase.
+  constexpr unsigned FULL = 0xFFFFFFFFu;
+  constexpr int NWARP = R_THREADS / 32;
+  const int lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_overflow = 0;
-  if (tid < S) {
-    const int scene = (e * st.K + st.cursor[e]) * S + tid;
-    const int shape = st.p_shape[scene];
-    s_shape[tid] = shape;
-    s_nv[tid] = shape ? st.shape_n[shape] : 0;
-    const uint32_t col = st.p_rgb[scene];
-    s_rgb[tid] = (int)col;
-    {  // colour - background per channel, three signed 10-bit fields
-      const int dr = (int)(col & 255u) - (int)(rd.bg & 255u);
-      const int dg = (int)((col >> 8) & 255u) - (int)((rd.bg >> 8) & 255u);
-      const int db = (int)((col >> 16) & 255u) - (int)((rd.bg >> 16) & 255u);
-      s_dr[tid] = (dr & 1023) | ((dg & 1023) << 10) | ((db & 1023) << 20);
-    }
-    s_px[tid] = st.pos_x[e * S + tid];
-    s_py[tid] = st.pos_y[e * S + tid];
-    s_m[0 * S + tid] = st.p_m00[scene];
-    s_m[1 * S + tid] = st.p_m01[scene];
-    s_m[2 * S + tid] = st.p_m10[scene];
-    s_m[3 * S + tid] = st.p_m11[scene];
-    s_nh[tid] = 0;
-    s_hasov[tid] = 0;
-  }
+  const int cur = st.cursor[e];
+  // tables first: their loads overlap the sprite records' dependent loads below
   for (int i = tid; i < rd.ncls_x * 33; i += R_THREADS) s_prefix[i] = rd.ax.prefix[i];
   for (int i = tid; i < n_rows; i += R_THREADS) s_nseg[i] = 0;
   for (int i = tid; i < rd.W; i += R_THREADS)
@@ -226,162 +219,165 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, uint8_t *__restri
   for (int i = tid; i < n_yo; i += R_THREADS)
     s_ywin[i] = (uint32_t)(uint16_t)rd.ay.win_min[yo_b0 + i] | ((uint32_t)rd.ay.win_len[yo_b0 + i] << 16) |
                 ((uint32_t)rd.ay.win_cls[yo_b0 + i] << 24);
-  __syncthreads();
-
-  // ---- phase A1: integer canvas vertices ----------------------------------------
-  for (int t = tid; t < S * EV; t += R_THREADS) {
-    const int s = t / EV, i = t % EV;
-    if (i < s_nv[s]) {
-      const double *v = st.shape_verts + ((size_t)s_shape[s] * EV + i) * 2;
-      const double vx = v[0], vy = v[1];
+  for (int s = warp; s < S; s += NWARP) {
+    // sprite record of this env's current scene (warp-uniform loads)
+    const int scene = (e * st.K + cur) * S + s;
+    const int shape = st.p_shape[scene];
+    const uint32_t col = st.p_rgb[scene];
+    const double px = st.pos_x[e * S + s], py = st.pos_y[e * S + s];
+    const double m00 = st.p_m00[scene], m01 = st.p_m01[scene];
+    const double m10 = st.p_m10[scene], m11 = st.p_m11[scene];
+    const int nv = shape ? st.shape_n[shape] : 0;
+    const int t = s * EV + lane;
+    // integer canvas vertex of this lane
+    int ivx = 0, ivy = 0;
+    if (lane < nv) {
+      const double2 v = reinterpret_cast<const double2 *>(st.shape_verts)[(size_t)shape * EV + lane];
       // centred path (sprite.py:96-101): (a*x + c*y) + 0 ; world (sprite.py:128-133): + pos
-      const double cx = __dadd_rn(__dadd_rn(__dmul_rn(s_m[0 * S + s], vx), __dmul_rn(s_m[1 * S + s], vy)), 0.0);
-      const double cy = __dadd_rn(__dadd_rn(__dmul_rn(s_m[2 * S + s], vx), __dmul_rn(s_m[3 * S + s], vy)), 0.0);
-      const double wx = __dadd_rn(cx, s_px[s]), wy = __dadd_rn(cy, s_py[s]);
+      const double cx = __dadd_rn(__dadd_rn(__dmul_rn(m00, v.x), __dmul_rn(m01, v.y)), 0.0);
+      const double cy = __dadd_rn(__dadd_rn(__dmul_rn(m10, v.x), __dmul_rn(m11, v.y)), 0.0);
+      const double wx = __dadd_rn(cx, px), wy = __dadd_rn(cy, py);
       // canvas_size * vertices (pil_renderer.py:81), then Pillow's (int) cast
-      s_ivx[t] = __double2int_rz(__dmul_rn((double)rd.CW, wx));
-      s_ivy[t] = __double2int_rz(__dmul_rn((double)rd.CH, wy));
+      ivx = __double2int_rz(__dmul_rn((double)rd.CW, wx));
+      ivy = __double2int_rz(__dmul_rn((double)rd.CH, wy));
     }
-  }
-  __syncthreads();
-
-  // ---- phase A2: edge records (Pillow add_edge) + per-sprite extents -------------
-  for (int t = tid; t < S * EV; t += R_THREADS) {
-    const int s = t / EV, i = t % EV;
-    const int nv = s_nv[s];
-    int flag = 0;
-    if (i < nv) {
-      const int j = (i + 1 == nv) ? 0 : i + 1;
-      const int x0 = s_ivx[s * EV + i], y0 = s_ivy[s * EV + i];
-      const int x1 = s_ivx[s * EV + j], y1 = s_ivy[s * EV + j];
-      // the closing edge exists only if the last vertex differs from the first
-      const bool exists = (i + 1 < nv) || (x0 != x1 || y0 != y1);
-      if (exists) {
-        e_x0[t] = x0;
-        e_y0[t] = y0;
-        if (y0 == y1) {  // horizontal: drawn directly as hline(xmin, y, xmax)
-          flag = 1;
-          if (y0 >= 0 && y0 < rd.CH) {
-            const int xs = max(min(x0, x1), 0), xe = min(max(x0, x1), rd.CW - 1);
-            if (xs <= xe) {
-              const int slot = atomicAdd(&s_nh[s], 1);
-              short *h = s_hl + ((size_t)s * EV + slot) * 3;
-              h[0] = (short)y0; h[1] = (short)xs; h[2] = (short)xe;
-            }
-          }
-        } else {
-          flag = 2;
-          e_ymin[t] = min(y0, y1);
-          e_ymax[t] = max(y0, y1);
-          e_dx[t] = __fdiv_rn((float)(x1 - x0), (float)(y1 - y0));
-        }
-      }
+    // edge lane -> lane+1 (Pillow add_edge); the closing edge exists only if the last vertex
+    // differs from the first
+    const int jn = (lane + 1 >= nv) ? 0 : lane + 1;
+    const int x0 = ivx, y0 = ivy;
+    const int x1 = __shfl_sync(FULL, ivx, jn), y1 = __shfl_sync(FULL, ivy, jn);
+    const bool exists = lane < nv && ((lane + 1 < nv) || (x0 != x1 || y0 != y1));
+    const bool scanned = exists && y0 != y1;
+    const int ymin = min(y0, y1), ymax = max(y0, y1);
+    const float dx = scanned ? __fdiv_rn((float)(x1 - x0), (float)(y1 - y0)) : 0.0f;
+    // horizontal edges are drawn directly as hline(xmin, y, xmax)
+    const int hxs = max(min(x0, x1), 0), hxe = min(max(x0, x1), rd.CW - 1);
+    const bool hline = exists && y0 == y1 && y0 >= 0 && y0 < rd.CH && hxs <= hxe;
+    const unsigned hmask = __ballot_sync(FULL, hline);
+    if (hline) {
+      short *h = s_hl + ((size_t)s * EV + __popc(hmask & ((1u << lane) - 1u))) * 3;
+      h[0] = (short)y0; h[1] = (short)hxs; h[2] = (short)hxe;
     }
-    e_flag[t] = (uint8_t)flag;
     // rows the edge crosses, clamped to int16 (canvas rows are < 4096); empty if not scanned
-    e_yr[t] = flag == 2 ? ((uint32_t)(uint16_t)(short)max(e_ymin[t], -32768) |
-                           ((uint32_t)(uint16_t)(short)min(e_ymax[t], 32767) << 16))
-                        : 0x80007FFFu;
+    const uint32_t yr = scanned ? ((uint32_t)(uint16_t)(short)max(ymin, -32768) |
+                                   ((uint32_t)(uint16_t)(short)min(ymax, 32767) << 16))
+                                : 0x80007FFFu;
+    e_x0[t] = x0;
+    e_y0[t] = y0;
+    e_dx[t] = dx;
+    e_yr[t] = yr;
     e_ovs[t] = nanf("");
     e_ove[t] = nanf("");
-    e_jks[t] = -1;
-    e_jke[t] = -1;
-    e_own_s[t] = -1;
-    e_own_e[t] = -1;
-  }
-  if (tid < S) {
-    const int nv = s_nv[tid];
-    int xmn = INT_MAX, xmx = INT_MIN, ymn = INT_MAX, ymx = INT_MIN;
-    for (int i = 0; i < nv; ++i) {
-      const int x = s_ivx[tid * EV + i], y = s_ivy[tid * EV + i];
-      xmn = min(xmn, x); xmx = max(xmx, x); ymn = min(ymn, y); ymx = max(ymx, y);
-    }
-    s_xmin[tid] = xmn; s_xmax[tid] = xmx; s_gymin[tid] = ymn; s_gymax[tid] = ymx;
+    // extents over the vertices
+    const bool isv = lane < nv;
+    const int xmn = __reduce_min_sync(FULL, isv ? ivx : INT_MAX), xmx = __reduce_max_sync(FULL, isv ? ivx : INT_MIN);
+    const int ymn = __reduce_min_sync(FULL, isv ? ivy : INT_MAX), ymx = __reduce_max_sync(FULL, isv ? ivy : INT_MIN);
     // Pillow: ymin = min(ysize-1, edges), ymax = max(0, edges); then clip to [0, ysize]
-    int pymin = min(rd.CH - 1, ymn), pymax = max(0, ymx);
-    pymin = max(pymin, 0);
-    pymax = min(pymax, rd.CH);
-    s_pymin[tid] = pymin; s_pymax[tid] = pymax;
-    {
-      const int r0 = max(pymin, row_b0), r1 = min(min(pymax, rd.CH - 1), row_b1 - 1);
-      s_r0[tid] = r0;
-      s_rcnt[tid] = (nv > 0 && r1 >= r0) ? (r1 - r0 + 1) : 0;
+    const int pymin = max(min(rd.CH - 1, ymn), 0), p_ymax = min(max(0, ymx), rd.CH);
+    const int r0 = max(pymin, row_b0), r1 = min(min(p_ymax, rd.CH - 1), row_b1 - 1);
+    const int rcnt = (nv > 0 && r1 >= r0) ? (r1 - r0 + 1) : 0;
+    // active-edge masks of eight equal row buckets: B1 only looks at the edges of its bucket
+    const int bsh = rcnt > 8 ? (32 - __clz(rcnt - 1) - 3) : 0;
+    unsigned my_bucket = 0;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const int lo = r0 + (b << bsh), hi = lo + (1 << bsh) - 1;
+      const unsigned m = __ballot_sync(FULL, scanned && ymin <= hi && ymax >= lo);
+      if (lane == b) my_bucket = m;
     }
-    // output region whose 2-D tap window can see this sprite's bounding box
-    short yo0 = 0, yo1 = -1, xo0 = 0, xo1 = -1;
-    if (nv > 0 && xmx >= 0 && xmn < rd.CW && ymx >= 0 && ymn < rd.CH) {
-      const int cx0 = max(xmn, 0), cx1 = min(xmx, rd.CW - 1);
-      const int cy0 = max(ymn, 0), cy1 = min(ymx, rd.CH - 1);
-      xo0 = rd.ax.first_out[cx0]; xo1 = rd.ax.last_out[cx1];
-      yo0 = max((int)rd.ay.first_out[cy0], yo_b0);
-      yo1 = min((int)rd.ay.last_out[cy1], yo_b1 - 1);
-    }
-    s_region[tid * 4 + 0] = yo0; s_region[tid * 4 + 1] = yo1;
-    s_region[tid * 4 + 2] = xo0; s_region[tid * 4 + 3] = xo1;
-    // tile plan: equal row blocks whose canvas rows (<= ny*aa + 32) fit the H buffer, equal
-    // column blocks of at most TILE_X_MAX (columns need no halo, rows do)
-    int pny = 1, pnx = 1;
-    if (yo1 >= yo0 && xo1 >= xo0) {
-      const int rh = yo1 - yo0 + 1, rw = xo1 - xo0 + 1;
-      const int ny_cap = max(1, (HT_ROWS - 32) / rd.aa + 1);  // (ny-1)*aa + len <= HT_ROWS
-      const int nty = (rh + ny_cap - 1) / ny_cap;
-      pny = (rh + nty - 1) / nty;
-      const int ntx = (rw + TILE_X_MAX - 1) / TILE_X_MAX;
-      pnx = (rw + ntx - 1) / ntx;
-    }
-    s_pny[tid] = pny; s_pnx[tid] = pnx;
-    s_pinv[tid] = (int)((1u << 20) / (uint32_t)pnx + 1u);  // it / pnx == (it * inv) >> 20 for it < 2^20 / pnx
-    s_pinvh[tid] = (int)((1u << 20) / (uint32_t)((pnx + 1) >> 1) + 1u);
-  }
-  __syncthreads();
+    if (lane < 8) s_emask[s * 8 + lane] = my_bucket;
+    __syncwarp();  // the edge table of this sprite is visible to the join search below
 
-  // ---- phase A3: corner joins ("connect discontiguous corners") ---------------------
-  // Edge i and the FIRST earlier edge k that leaves the same corner in the same x
-  // direction -- both starting on row y, or both ending on the polygon's last row --
-  // move k's crossing on that row towards the adjacent row's span (oracle/
-  // sw_raster_oracle.c).  Found per edge here, applied in B1.
-  for (int t = tid; t < S * EV; t += R_THREADS) {
-    if (e_flag[t] != 2) continue;
-    const float dx = e_dx[t];
-    if (dx == 0.0f) continue;
-    const int s = t / EV, i = t % EV, base = s * EV;
-    const int p_ymax = s_pymax[s];
+    // corner joins ("connect discontiguous corners"): edge i and the FIRST earlier edge k
+    // that leaves the same corner in the same x direction -- both starting on row y, or both
+    // ending on the polygon's last row -- move k's crossing on that row towards the adjacent
+    // row's span (oracle/sw_raster_oracle.c).  Applied in B1 through e_ovs / e_ove.
+    const unsigned lt = (1u << lane) - 1u;
+    const unsigned pos = __ballot_sync(FULL, scanned && dx > 0.0f);
+    const unsigned neg = __ballot_sync(FULL, scanned && dx < 0.0f);
+    const unsigned same_dir = dx > 0.0f ? pos : (dx < 0.0f ? neg : 0u);
+    const unsigned start_grp = __match_any_sync(FULL, scanned ? (int)(short)(yr & 0xFFFFu) : (0x40000000 | lane));
+    const unsigned end_grp = __ballot_sync(FULL, scanned && (int)(short)(yr >> 16) == p_ymax);
+    bool any_join = false;
+#pragma unroll
     for (int pass = 0; pass < 2; ++pass) {
-      const int y = pass == 0 ? e_ymin[t] : p_ymax;
-      if (pass == 1 && e_ymax[t] != p_ymax) break;
-      if (y < 0 || y >= rd.CH) continue;
-      const float x = edge_x_at(y, e_y0[t], dx, e_x0[t]);
-      for (int k = 0; k < i; ++k) {
-        const int u = base + k;
-        const uint32_t yr = e_yr[u];  // empty range for edges that are not scanned
-        if ((pass == 0 ? (int)(short)(yr & 0xFFFFu) : (int)(short)(yr >> 16)) != y) continue;
-        if (e_flag[u] != 2) continue;
-        const float odx = e_dx[u];
-        if ((dx > 0.0f && odx <= 0.0f) || (dx < 0.0f && odx >= 0.0f)) continue;
-        const float ox = edge_x_at(y, e_y0[u], odx, e_x0[u]);
-        if (roundf(x) != roundf(ox)) continue;
-        const int off = (y == p_ymax) ? -1 : 1;
-        const float adj = edge_x_at(y + off, e_y0[t], dx, e_x0[t]);
-        const float adjo = edge_x_at(y + off, e_y0[u], odx, e_x0[u]);
-        const bool right = (y == e_ymax[t]) ? (dx < 0.0f) : (dx > 0.0f);
-        float nv = right ? __fsub_rn(fminf(adj, adjo), 1.0f) : __fadd_rn(fmaxf(adj, adjo), 1.0f);
-        nv = floorf(__fadd_rn(nv, 0.5f));
-        nv = right ? fmaxf(nv, x) : fminf(nv, x);
-        // several later edges may pick the same k: the last one in table order wins
-        if (pass == 0) { e_jks[t] = (int8_t)k; e_jvs[t] = nv; atomicMax(&e_own_s[base + k], i); }
-        else { e_jke[t] = (int8_t)k; e_jve[t] = nv; atomicMax(&e_own_e[base + k], i); }
-        break;
+      const int y = pass == 0 ? ymin : p_ymax;
+      unsigned cand = (pass == 0 ? start_grp : end_grp) & lt & same_dir;
+      if (!scanned || (pass == 1 && ymax != p_ymax) || y < 0 || y >= rd.CH) cand = 0;
+      int jk = -1;
+      float jv = 0.0f;
+      if (cand) {
+        const float x = edge_x_at(y, y0, dx, x0);
+        while (cand) {
+          const int k = __ffs(cand) - 1;
+          cand &= cand - 1;
+          const int u = s * EV + k;
+          const float odx = e_dx[u];
+          const int oy0 = e_y0[u], ox0 = e_x0[u];
+          const float ox = edge_x_at(y, oy0, odx, ox0);
+          if (roundf(x) != roundf(ox)) continue;
+          const int off = (y == p_ymax) ? -1 : 1;
+          const float adj = edge_x_at(y + off, y0, dx, x0);
+          const float adjo = edge_x_at(y + off, oy0, odx, ox0);
+          const bool right = (y == ymax) ? (dx < 0.0f) : (dx > 0.0f);
+          float nvx = right ? __fsub_rn(fminf(adj, adjo), 1.0f) : __fadd_rn(fmaxf(adj, adjo), 1.0f);
+          nvx = floorf(__fadd_rn(nvx, 0.5f));
+          jv = right ? fmaxf(nvx, x) : fminf(nvx, x);
+          jk = k;
+          break;
+        }
       }
+      // several later edges may pick the same k: the last one in table order wins
+      const unsigned grp = __match_any_sync(FULL, jk >= 0 ? jk : (64 + lane));
+      if (jk >= 0 && (grp >> lane) == 1u) {
+        (pass == 0 ? e_ovs : e_ove)[s * EV + jk] = jv;
+      }
+      any_join |= __any_sync(FULL, jk >= 0);
+    }
+
+    if (lane == 0) {
+      s_nv[s] = nv;
+      {  // colour - background per channel, three signed 10-bit fields
+        const int dr = (int)(col & 255u) - (int)(rd.bg & 255u);
+        const int dg = (int)((col >> 8) & 255u) - (int)((rd.bg >> 8) & 255u);
+        const int db = (int)((col >> 16) & 255u) - (int)((rd.bg >> 16) & 255u);
+        s_dr[s] = (dr & 1023) | ((dg & 1023) << 10) | ((db & 1023) << 20);
+      }
+      s_nh[s] = __popc(hmask);
+      s_hasov[s] = any_join ? 1 : 0;
+      s_pymax[s] = p_ymax;
+      s_r0[s] = r0;
+      s_rcnt[s] = rcnt;
+      s_bsh[s] = bsh;
+      // output region whose 2-D tap window can see this sprite's bounding box
+      short yo0 = 0, yo1 = -1, xo0 = 0, xo1 = -1;
+      if (nv > 0 && xmx >= 0 && xmn < rd.CW && ymx >= 0 && ymn < rd.CH) {
+        const int cx0 = max(xmn, 0), cx1 = min(xmx, rd.CW - 1);
+        const int cy0 = max(ymn, 0), cy1 = min(ymx, rd.CH - 1);
+        xo0 = rd.ax.first_out[cx0]; xo1 = rd.ax.last_out[cx1];
+        yo0 = max((int)rd.ay.first_out[cy0], yo_b0);
+        yo1 = min((int)rd.ay.last_out[cy1], yo_b1 - 1);
+      }
+      s_region[s * 4 + 0] = yo0; s_region[s * 4 + 1] = yo1;
+      s_region[s * 4 + 2] = xo0; s_region[s * 4 + 3] = xo1;
+      // tile plan: equal row blocks whose canvas rows (<= ny*aa + 32) fit the H buffer, equal
+      // column blocks of at most TILE_X_MAX (columns need no halo, rows do)
+      int pny = 1, pnx = 1;
+      if (yo1 >= yo0 && xo1 >= xo0) {
+        const int rh = yo1 - yo0 + 1, rw = xo1 - xo0 + 1;
+        const int ny_cap = max(1, (HT_ROWS - 32) / rd.aa + 1);  // (ny-1)*aa + len <= HT_ROWS
+        const int nty = (rh + ny_cap - 1) / ny_cap;
+        pny = (rh + nty - 1) / nty;
+        const int ntx = (rw + TILE_X_MAX - 1) / TILE_X_MAX;
+        pnx = (rw + ntx - 1) / ntx;
+      }
+      s_pny[s] = pny; s_pnx[s] = pnx;
+      s_pinv[s] = (int)((1u << 20) / (uint32_t)pnx + 1u);  // it / pnx == (it * inv) >> 20 for it < 2^20 / pnx
+      s_pinvh[s] = (int)((1u << 20) / (uint32_t)((pnx + 1) >> 1) + 1u);
     }
   }
   __syncthreads();
-  for (int t = tid; t < S * EV; t += R_THREADS) {
-    const int i = t % EV, base = t - i;
-    const int ks = e_jks[t], ke = e_jke[t];
-    if (ks >= 0 && e_own_s[base + ks] == i) { e_ovs[base + ks] = e_jvs[t]; s_hasov[t / EV] = 1; }
-    if (ke >= 0 && e_own_e[base + ke] == i) { e_ove[base + ke] = e_jve[t]; s_hasov[t / EV] = 1; }
-  }
-  __syncthreads();
+  SWB_MARK(3);
 
   // ---- phase B: visible segments per canvas row -----------------------------------------
   // B1 (sprite, row)-parallel: Pillow's scan conversion of one canvas row of one sprite
@@ -401,26 +397,25 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, uint8_t *__restri
     uint32_t *s_spans = reinterpret_cast<uint32_t *>(smem + L.off_scratch) + rows_used * CAP;
     const bool fits = rows_used * CAP * 4 + (s_hi - s_lo) * n_rows * M * 4 <= L.scratch_bytes;
     if (!fits) { s_overflow = 1; }
-    if (tid == 0) {
-      int off = 0;
-      for (int s = s_lo; s < s_hi; ++s) { s_roff[s] = off; off += s_rcnt[s]; }
-    }
-    __syncthreads();
+    SWB_MARK(4);
     // B1
     for (int t = tid; fits && t < rows_used; t += R_THREADS) {
       int s = s_lo, rem = t;
       while (rem >= s_rcnt[s]) { rem -= s_rcnt[s]; ++s; }
       const int y = s_r0[s] + rem;
-      const int base = s * EV, ne = s_nv[s], p_ymax = s_pymax[s];
+      const int base = s * EV, p_ymax = s_pymax[s];
       const bool hasov = s_hasov[s] != 0;
       float *xx = reinterpret_cast<float *>(smem + L.off_scratch) + (size_t)t * CAP;
       int j = 0;
       bool ovf = false;
-      for (int i = 0; i < ne; ++i) {
-        const uint32_t yr = e_yr[base + i];
+      // edges whose rows overlap this row's bucket, in table order
+      unsigned active = s_emask[s * 8 + (rem >> s_bsh[s])];
+      while (active) {
+        const int u = base + __ffs(active) - 1;
+        active &= active - 1;
+        const uint32_t yr = e_yr[u];
         const int ymin = (int)(short)(yr & 0xFFFFu), ymax = (int)(short)(yr >> 16);
         if (y < ymin || y > ymax) continue;
-        const int u = base + i;
         float x = edge_x_at(y, e_y0[u], e_dx[u], e_x0[u]);
         if (hasov) {  // corner-join overrides (rare: acute same-direction corners only)
           if (y == ymin) { const float o = e_ovs[u]; if (!isnan(o)) x = o; }
@@ -494,6 +489,7 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, uint8_t *__restri
       if (ovf) s_overflow = 1;
     }
     __syncthreads();
+    SWB_MARK(5);
     // B2
     for (int ry = tid; fits && ry < n_rows; ry += R_THREADS) {
       const int y = row_b0 + ry;
@@ -536,6 +532,7 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, uint8_t *__restri
       if (ovf) s_overflow = 1;
     }
     __syncthreads();
+    SWB_MARK(6);
     s_hi = s_lo;
   }
 
@@ -553,6 +550,7 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, uint8_t *__restri
     }
   }
   __syncthreads();
+  SWB_MARK(7);
 
   // ---- phase C: per sprite region, in tiles sized to the H buffer -----------------------
   // A region of h x w outputs is cut into ceil(h/32) row blocks and, per row block, into as
@@ -635,6 +633,7 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, uint8_t *__restri
           }
         }
         __syncthreads();
+        SWB_MARK(8);
         // ---- V pass: item = (output row ly, column c) ----
         for (int it = tid; it < ny * nx; it += R_THREADS) {
           const int ly = (int)(((uint32_t)it * inv_nx) >> 20);
@@ -689,6 +688,7 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, uint8_t *__restri
           px[2] = (uint8_t)clip8_q22(ab);
         }
         __syncthreads();
+        SWB_MARK(9);
       }
     }
   }
@@ -715,6 +715,7 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, uint8_t *__restri
   }
   // several bands of one env may race here, but they all OR in the same bit
   if (tid == 0 && s_overflow) st.render_status[e] |= (uint8_t)SWB_ENV_SPAN_OVERFLOW;
+  SWB_MARK(10);
 }
 
 }  // namespace swb
