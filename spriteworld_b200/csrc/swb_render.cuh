@@ -212,7 +212,7 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, uint8_t *__restri
   const int cur = st.cursor[e];
   // tables first: their loads overlap the sprite records' dependent loads below
   for (int i = tid; i < rd.ncls_x * 33; i += R_THREADS) s_prefix[i] = rd.ax.prefix[i];
-  for (int i = tid; i < n_rows; i += R_THREADS) s_nseg[i] = 0;
+  for (int i = tid; i < (n_rows + 3) / 4; i += R_THREADS) reinterpret_cast<uint32_t *>(s_nseg)[i] = 0u;
   for (int i = tid; i < rd.W; i += R_THREADS)
     s_xwin[i] = (uint32_t)(uint16_t)rd.ax.win_min[i] | ((uint32_t)rd.ax.win_len[i] << 16) |
                 ((uint32_t)rd.ax.win_cls[i] << 24);
@@ -387,6 +387,10 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, uint8_t *__restri
   // Sprites are taken front to back in chunks whose scratch (crossing lists + spans) fits.
   for (int s_hi = S; s_hi > 0;) {
     int s_lo = s_hi, rows_used = 0;
+    if (s_hi == S && S <= 32) {  // common case: every sprite fits in one chunk
+      const int rows_all = __reduce_add_sync(FULL, lane < S ? s_rcnt[lane] : 0);
+      if (rows_all * CAP * 4 + S * n_rows * M * 4 <= L.scratch_bytes) { s_lo = 0; rows_used = rows_all; }
+    }
     while (s_lo > 0) {
       const int rows_next = rows_used + s_rcnt[s_lo - 1];
       const int need = rows_next * CAP * 4 + (s_hi - s_lo + 1) * n_rows * M * 4;
@@ -541,8 +545,13 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, uint8_t *__restri
     const int n_bytes = n_yo * rd.W * 3;
     if (r == g && g == b) {
       const uint32_t w = r * 0x01010101u;
-      uint32_t *f32 = reinterpret_cast<uint32_t *>(s_frame);
-      for (int i = tid; i < (n_bytes + 3) / 4; i += R_THREADS) f32[i] = w;
+      if ((n_bytes & 15) == 0) {
+        uint4 *f128 = reinterpret_cast<uint4 *>(s_frame);
+        for (int i = tid; i < (n_bytes >> 4); i += R_THREADS) f128[i] = make_uint4(w, w, w, w);
+      } else {
+        uint32_t *f32 = reinterpret_cast<uint32_t *>(s_frame);
+        for (int i = tid; i < (n_bytes + 3) / 4; i += R_THREADS) f32[i] = w;
+      }
     } else {
       for (int i = tid; i < n_yo * rd.W; i += R_THREADS) {
         s_frame[3 * i] = (uint8_t)r; s_frame[3 * i + 1] = (uint8_t)g; s_frame[3 * i + 2] = (uint8_t)b;
