@@ -279,7 +279,7 @@ def main():
   cpu = None
   if not args.no_cpu_baseline:
     n_cpu_steps = 25
-    v, cores, dt, n = cpu_reference(wl, 8 * (os.cpu_count() or 1), n_cpu_steps, 3)
+    v, cores, dt, n = cpu_reference(wl, 64 * (os.cpu_count() or 1), n_cpu_steps, 3)
     cpu = dict(value=v, unit=UNIT, cores=cores, kind='port',
                sample='%d envs x %d steps of %s, %.1f s wall, oracle C port of the reference '
                       'path (Pillow polygon fill + LANCZOS restated), one thread per core'

@@ -499,11 +499,9 @@ SWO_API void swo_task_eval(const swo_env_cfg *cfg, const swo_sprite *sp, int S, 
 /* ---- renderer: renderers/pil_renderer.py:67-91 ---------------------------- */
 
 /* frame: H x W x 3, already flipped (np.flipud).  canvas scratch: (aa*H)*(aa*W)*3 bytes. */
-SWO_API void swo_render(const swo_raster_cfg *rc, const swo_shape_table *tab, const swo_sprite *sp,
-                        int S, uint8_t *frame, uint8_t *canvas) {
+static void render_ws(const swo_raster_cfg *rc, const swo_shape_table *tab, const swo_sprite *sp,
+                      int S, uint8_t *frame, uint8_t *canvas, uint8_t *hbuf, uint8_t *small) {
   int CW = rc->anti_aliasing * rc->width, CH = rc->anti_aliasing * rc->height;
-  int own = 0;
-  if (!canvas) { canvas = (uint8_t *)malloc((size_t)CW * CH * 3); own = 1; }
   for (size_t i = 0; i < (size_t)CW * CH; i++) { /* canvas.paste(bg) :79 */
     canvas[3 * i] = rc->bg[0]; canvas[3 * i + 1] = rc->bg[1]; canvas[3 * i + 2] = rc->bg[2];
   }
@@ -521,13 +519,40 @@ SWO_API void swo_render(const swo_raster_cfg *rc, const swo_shape_table *tab, co
     }
     swo_polygon_fill(canvas, CW, CH, xy, n, sp[s].rgb, 1);
   }
-  uint8_t *small = (uint8_t *)malloc((size_t)rc->width * rc->height * 3);
-  swo_lanczos_resize(canvas, CW, CH, small, rc->width, rc->height, NULL); /* :84 */
+  swo_lanczos_resize(canvas, CW, CH, small, rc->width, rc->height, hbuf); /* :84 */
   size_t row = (size_t)rc->width * 3;
   for (int y = 0; y < rc->height; y++) /* np.flipud :90 */
     memcpy(frame + (size_t)(rc->height - 1 - y) * row, small + (size_t)y * row, row);
-  free(small);
-  if (own) free(canvas);
+}
+
+/* Scratch of one render: the aa-times canvas, the horizontal-pass image and the unflipped
+ * frame.  Kept per thread and only ever grown: the batch driver is called once per step from
+ * every worker thread, and a 300 KB malloc/free pair per call goes through mmap/munmap, which
+ * serialises the threads on the process's address-space lock. */
+static __thread uint8_t *tls_ws = NULL;
+static __thread size_t tls_ws_cap = 0;
+
+static void workspace(const swo_raster_cfg *rc, uint8_t **canvas, uint8_t **hbuf, uint8_t **small) {
+  size_t CW = (size_t)rc->anti_aliasing * rc->width, CH = (size_t)rc->anti_aliasing * rc->height;
+  size_t n_canvas = CW * CH * 3, n_h = CH * rc->width * 3, n_small = (size_t)rc->width * rc->height * 3;
+  size_t need = n_canvas + n_h + n_small;
+  if (need > tls_ws_cap) {
+    free(tls_ws);
+    tls_ws = (uint8_t *)malloc(need);
+    tls_ws_cap = need;
+  }
+  *canvas = tls_ws;
+  *hbuf = tls_ws + n_canvas;
+  *small = tls_ws + n_canvas + n_h;
+}
+
+/* frame: H x W x 3, already flipped (np.flipud).  canvas: optional caller scratch of
+ * (aa*H)*(aa*W)*3 bytes that receives the anti-aliasing canvas (tests look at it). */
+SWO_API void swo_render(const swo_raster_cfg *rc, const swo_shape_table *tab, const swo_sprite *sp,
+                        int S, uint8_t *frame, uint8_t *canvas) {
+  uint8_t *ws_canvas, *hbuf, *small;
+  workspace(rc, &ws_canvas, &hbuf, &small);
+  render_ws(rc, tab, sp, S, frame, canvas ? canvas : ws_canvas, hbuf, small);
 }
 
 /* ---- environment: environment.py:74-108 ----------------------------------- */
@@ -570,11 +595,10 @@ SWO_API int swo_batch_step(const swo_env_cfg *cfg, const swo_shape_table *tab,
                            uint8_t *frames, int e0, int e1) {
   size_t astride = cfg->action_kind == SWO_ACT_EMBODIED ? 2 * sizeof(int32_t)
                    : (action_is_f32 ? 4 * sizeof(float) : 4 * sizeof(double));
-  uint8_t *canvas = NULL;
+  uint8_t *canvas = NULL, *hbuf = NULL, *small = NULL;
   size_t fbytes = 0;
   if (rc && frames) {
-    canvas = (uint8_t *)malloc((size_t)rc->anti_aliasing * rc->width * rc->anti_aliasing *
-                               rc->height * 3);
+    workspace(rc, &canvas, &hbuf, &small);
     fbytes = (size_t)rc->width * rc->height * 3;
   }
   int bad = 0;
@@ -598,9 +622,8 @@ SWO_API int swo_batch_step(const swo_env_cfg *cfg, const swo_shape_table *tab,
       if (r) { bad = r; continue; }
       if (step_type[e] == SWO_STEP_LAST) reset_next[e] = 1;
     }
-    if (canvas) swo_render(rc, tab, sp, S, frames + fbytes * e, canvas);
+    if (canvas) render_ws(rc, tab, sp, S, frames + fbytes * e, canvas, hbuf, small);
   }
-  free(canvas);
   return bad;
 }
 
