@@ -70,7 +70,25 @@ class ClockSampler(threading.Thread):
                 samples=len(sm))
 
 
-def cpu_reference(wl, n_sample_envs, steps, warmup, seed=1000):
+def usable_cores():
+  """Host CPUs this process may actually use: the affinity mask capped by the cgroup CPU
+  quota (cpu.max).  On the GPU boxes 128 logical CPUs are visible but the container's quota
+  is 16; more threads than that only add throttling."""
+  try:
+    n = len(os.sched_getaffinity(0))
+  except AttributeError:
+    n = os.cpu_count() or 1
+  try:
+    with open('/sys/fs/cgroup/cpu.max') as f:
+      quota, period = f.read().split()[:2]
+    if quota != 'max':
+      n = max(1, min(n, int(round(int(quota) / float(period)))))
+  except (OSError, ValueError):
+    pass
+  return n
+
+
+def cpu_reference(wl, n_sample_envs, steps, warmup, seed=1000, cores=None):
   """The reference's algorithm on the host cores: oracle port (C restatement of the
   reference path incl. Pillow's polygon fill and LANCZOS), one thread per core, each
   stepping its own slice of a bounded env sample.  Returns (env-steps/s, cores, seconds)."""
@@ -78,7 +96,7 @@ def cpu_reference(wl, n_sample_envs, steps, warmup, seed=1000):
   from oracle import oracle
   from spriteworld_b200 import constants
   from tests import fixtures
-  cores = os.cpu_count() or 1
+  cores = cores or usable_cores()
   n = max(cores, (n_sample_envs // cores) * cores)
   K = max(2, (steps + warmup) // wl.max_episode_length + 2)
   rng = np.random.RandomState(seed)
@@ -113,10 +131,11 @@ def run_reference_arm(args, wl):
   if rank != 0:
     return
   # each step = a bounded sample of the workload sized to finish within minutes
-  n_sample = 16 * (os.cpu_count() or 1)
+  n_sample = 128 * usable_cores()
   value, cores, dt, n = cpu_reference(wl, n_sample, args.steps, args.warmup)
-  sample = '%d envs x %d steps of %s on %d host threads (oracle C port of the reference path)' % (
-      n, args.steps, wl.name, cores)
+  sample = ('%d envs x %d steps of %s on %d host threads = usable cores (cgroup quota; %d logical '
+            'CPUs visible), oracle C port of the reference path' % (
+                n, args.steps, wl.name, cores, os.cpu_count() or 1))
   line = dict(
       impl='reference', metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus,
       steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * dt / args.steps,
@@ -279,11 +298,12 @@ def main():
   cpu = None
   if not args.no_cpu_baseline:
     n_cpu_steps = 25
-    v, cores, dt, n = cpu_reference(wl, 64 * (os.cpu_count() or 1), n_cpu_steps, 3)
+    v, cores, dt, n = cpu_reference(wl, 512 * usable_cores(), n_cpu_steps, 3)
     cpu = dict(value=v, unit=UNIT, cores=cores, kind='port',
                sample='%d envs x %d steps of %s, %.1f s wall, oracle C port of the reference '
-                      'path (Pillow polygon fill + LANCZOS restated), one thread per core'
-                      % (n, n_cpu_steps, wl.name, dt))
+                      'path (Pillow polygon fill + LANCZOS restated), one thread per usable core '
+                      '(affinity mask capped by the cgroup CPU quota; %d logical CPUs visible)'
+                      % (n, n_cpu_steps, wl.name, dt, os.cpu_count() or 1))
   value = world * E * args.steps / (ms * 1e-3)
   line = dict(
       metric=METRIC, value=value, unit=UNIT, frames_per_sec=value, n_gpus=world,

@@ -23,11 +23,9 @@ def main():
   import bench
   from spriteworld_b200 import workloads
   wl = workloads.WORKLOADS[args.workload]()
-  real = os.cpu_count()
-  print('host cpus: %s' % real)
+  print('host cpus: %s, usable (affinity and cgroup quota): %d' % (os.cpu_count(), bench.usable_cores()))
   for c in [int(x) for x in args.threads.split(',')]:
-    os.cpu_count = lambda c=c: c
-    v, cores, dt, n = bench.cpu_reference(wl, 16 * c, args.steps, 3)
+    v, cores, dt, n = bench.cpu_reference(wl, 16 * c, args.steps, 3, cores=c)
     print('threads %4d: %9.0f env-steps/s  (%.2f ms per env-step per thread, %d envs, %.1f s)' % (
         c, v, 1e3 * c / v, n, dt))
 
