@@ -194,12 +194,12 @@ def main():
         item[0].wait()
         inflight.remove(item)
 
-  def one_step(t):
+  def one_step(t, gather=True):
     slot, dst = t % n_ring, t % 2
     wait_for(lambda it: it[1] == slot)     # the gather that last read this ring buffer
     fr = ring[slot]
-    eng.step(actions[t], raster, fr)
-    if world > 1:
+    eng.step(actions[t % T], raster, fr)
+    if world > 1 and gather:
       # the single collective of the path: gather the rendered frames of every rank.  It
       # runs on NCCL's stream and overlaps the next step's compute.
       wait_for(lambda it: it[2] == dst)
@@ -236,6 +236,21 @@ def main():
     tms = torch.tensor([ms], device=dev)
     dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms = float(tms.item())
+
+  # SURVEY 8(e) asks for both numbers: the same steps with the frames left sharded
+  sharded = None
+  if world > 1:
+    evs0, evs1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    evs0.record()
+    for t in range(T, T + args.steps):
+      one_step(t, gather=False)
+    evs1.record()
+    barrier()
+    tms = torch.tensor([evs0.elapsed_time(evs1)], device=dev)
+    dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    sharded = dict(value=world * E * args.steps / (float(tms.item()) * 1e-3), unit=UNIT,
+                   ms_per_step=float(tms.item()) / args.steps)
 
   # dominant kernel alone: K launches of the render kernel, CUDA events on its stream
   evr0, evr1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -299,7 +314,8 @@ def main():
   if not args.no_cpu_baseline:
     n_cpu_steps = 25
     v, cores, dt, n = cpu_reference(wl, 512 * usable_cores(), n_cpu_steps, 3)
-    cpu = dict(value=v, unit=UNIT, cores=cores, kind='port',
+    v1 = cpu_reference(wl, 32, 10, 2, cores=1)[0]
+    cpu = dict(value=v, unit=UNIT, cores=cores, kind='port', single_core=v1,
                sample='%d envs x %d steps of %s, %.1f s wall, oracle C port of the reference '
                       'path (Pillow polygon fill + LANCZOS restated), one thread per usable core '
                       '(affinity mask capped by the cgroup CPU quota; %d logical CPUs visible)'
@@ -320,6 +336,8 @@ def main():
                     kernel='render_kernel', kernel_ms=render_ms,
                     algorithmic_bytes_per_launch=alg_bytes),
       cpu_baseline=cpu, e2e=e2e, gpu_launches=int(launches), clocks=clocks)
+  if sharded:
+    line['frames_sharded'] = sharded   # same steps without the frame gather
   print(json.dumps(line))
   if world > 1:
     dist.destroy_process_group()
