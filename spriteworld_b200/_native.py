@@ -59,8 +59,9 @@ class StepOut(ctypes.Structure):
               ('success', ctypes.c_void_p), ('status', ctypes.c_void_p)]
 
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'csrc',
-                         'libspriteworld_b200.so')
+# SPRITEWORLD_B200_LIB points at another build of the same library (debug / experiment builds)
+_LIB_PATH = os.environ.get('SPRITEWORLD_B200_LIB') or os.path.join(
+    os.path.dirname(os.path.abspath(__file__)), 'csrc', 'libspriteworld_b200.so')
 _lib = None
 
 

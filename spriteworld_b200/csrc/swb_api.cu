@@ -387,6 +387,7 @@ int swb_raster_create(swb_engine *eng, int32_t width, int32_t height, int32_t aa
   rd.max_spans = 1;
   rd.ncls_x = r->ax.n_cls;
   rd.ncls_y = r->ay.n_cls;
+  rd.ny_cap = std::max(1, (HT_ROWS - 32) / rd.aa + 1);
   rd.a5_cls = -1;
   for (int c = 0; c < r->ay.n_cls; ++c) {
     const int32_t *prog = r->ay.program.data() + (size_t)c * PROG_STRIDE;

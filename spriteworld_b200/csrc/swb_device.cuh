@@ -63,6 +63,7 @@ struct RasterDev {
   int n_bands;
   int max_spans;  // spans kept per (sprite, canvas row)
   int ncls_x, ncls_y;  // distinct tap vectors per axis
+  int ny_cap;  // output rows per render tile: (ny_cap-1)*aa + 32 canvas rows fit the H buffer
   // vertical-pass fast path: class id and the 13 distinct coefficients of the interior tap
   // vector of a 5x reduction (taps k and 28-k equal; 4,9,19,24,29 zero; 14 the centre)
   int a5_cls;

@@ -35,6 +35,7 @@
 namespace swb {
 
 constexpr int R_THREADS = 256;
+constexpr int H_NC = 2;           // output columns one H-pass thread owns
 constexpr int TILE_X_MAX = 20;    // output columns per tile = row stride of the H buffer
 constexpr int HT_ROWS = 112;      // canvas rows a tile's H buffer holds
 constexpr int HT_ITEMS = HT_ROWS * TILE_X_MAX;
@@ -133,6 +134,19 @@ __device__ __forceinline__ void add_span(int *lxs, int *lxe, int &n, int xs, int
   }
 }
 
+// c_inv20[d] = 2^20 / d + 1: x / d == (x * c_inv20[d]) >> 20 for 0 <= x < 2^20 / d (d <= 64)
+__constant__ uint32_t c_inv20[65] = {
+    0u, 1048577u, 524289u, 349526u, 262145u, 209716u, 174763u, 149797u,
+    131073u, 116509u, 104858u, 95326u, 87382u, 80660u, 74899u, 69906u,
+    65537u, 61681u, 58255u, 55189u, 52429u, 49933u, 47663u, 45591u,
+    43691u, 41944u, 40330u, 38837u, 37450u, 36158u, 34953u, 33826u,
+    32769u, 31776u, 30841u, 29960u, 29128u, 28340u, 27595u, 26887u,
+    26215u, 25576u, 24967u, 24386u, 23832u, 23302u, 22796u, 22311u,
+    21846u, 21400u, 20972u, 20561u, 20165u, 19785u, 19419u, 19066u,
+    18725u, 18397u, 18079u, 17773u, 17477u, 17190u, 16913u, 16645u,
+    16385u};
+__device__ __forceinline__ int div20(int x, int d) { return (int)(((uint32_t)x * c_inv20[d]) >> 20); }
+
 // Debug-only phase timers (nvcc -DSWB_PHASE_CLOCKS): thread 0 of every CTA adds the cycles
 // between consecutive marks to g_phase_clk[id].  Not part of the shipped library.
 #ifdef SWB_PHASE_CLOCKS
@@ -164,8 +178,8 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, uint8_t *__restri
   int *s_nv = reinterpret_cast<int *>(smem + L.off_meta);
   int *s_pymax = s_nv + S, *s_r0 = s_pymax + S, *s_rcnt = s_r0 + S, *s_nh = s_rcnt + S;
   int *s_bsh = s_nh + S, *s_dr = s_bsh + S;
-  int *s_pny = s_dr + S, *s_pnx = s_pny + S, *s_pinv = s_pnx + S;
-  int *s_pinvh = s_pinv + S, *s_hasov = s_pinvh + S;
+  int *s_pny = s_dr + S, *s_pnx = s_pny + S;
+  int *s_pinvh = s_pnx + S, *s_hasov = s_pinvh + S;
   unsigned *s_emask = reinterpret_cast<unsigned *>(s_hasov + S);  // [S][8] active edges per row bucket
   // edge table: start vertex, slope, corner-join overrides on the first / last row
   int *e_x0 = reinterpret_cast<int *>(smem + L.off_edge_i);
@@ -364,16 +378,16 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, uint8_t *__restri
       // column blocks of at most TILE_X_MAX (columns need no halo, rows do)
       int pny = 1, pnx = 1;
       if (yo1 >= yo0 && xo1 >= xo0) {
+        // regions are at most band_rows x W outputs; the reciprocal table covers divisors <= 64
         const int rh = yo1 - yo0 + 1, rw = xo1 - xo0 + 1;
-        const int ny_cap = max(1, (HT_ROWS - 32) / rd.aa + 1);  // (ny-1)*aa + len <= HT_ROWS
-        const int nty = (rh + ny_cap - 1) / ny_cap;
-        pny = (rh + nty - 1) / nty;
-        const int ntx = (rw + TILE_X_MAX - 1) / TILE_X_MAX;
-        pnx = (rw + ntx - 1) / ntx;
+        const int ny_cap = rd.ny_cap;  // (ny-1)*aa + len <= HT_ROWS
+        const int nty = ny_cap <= 64 ? div20(rh + ny_cap - 1, ny_cap) : 1;
+        pny = nty <= 64 ? div20(rh + nty - 1, nty) : (rh + nty - 1) / nty;
+        const int ntx = div20(rw + TILE_X_MAX - 1, TILE_X_MAX);
+        pnx = ntx <= 64 ? div20(rw + ntx - 1, ntx) : (rw + ntx - 1) / ntx;
       }
       s_pny[s] = pny; s_pnx[s] = pnx;
-      s_pinv[s] = (int)((1u << 20) / (uint32_t)pnx + 1u);  // it / pnx == (it * inv) >> 20 for it < 2^20 / pnx
-      s_pinvh[s] = (int)((1u << 20) / (uint32_t)((pnx + 1) >> 1) + 1u);
+      s_pinvh[s] = (int)c_inv20[(pnx + H_NC - 1) / H_NC];
     }
   }
   __syncthreads();
@@ -579,26 +593,30 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, uint8_t *__restri
       const int nr = tr1 - tr0;
       for (int tx0 = rxo0; tx0 <= rxo1; tx0 += nx_blk) {
         const int nx = min(nx_blk, rxo1 - tx0 + 1);
-        const uint32_t inv_nx = nx == nx_blk ? (uint32_t)s_pinv[s] : (1u << 20) / (uint32_t)nx + 1u;
-        // ---- H pass: a thread owns two columns (c, c + half) and strides over the canvas
-        // rows, so the window start/length, tap prefix table and bg*K are loop invariants and
-        // the row's segment records are decoded once for both columns ----
+        // ---- H pass: a thread owns NC columns (c0, c0 + cs, ...) and strides over the canvas
+        // rows, so the window start/length and tap prefix table are loop invariants and the
+        // row's segment records are decoded once for all its columns ----
         {
-          const int half = (nx + 1) >> 1;
-          const uint32_t inv_half = nx == nx_blk ? (uint32_t)s_pinvh[s] : (1u << 20) / (uint32_t)half + 1u;
-          const int rgroup = (int)(((uint32_t)tid * inv_half) >> 20);  // tid / half
-          const int c0 = tid - rgroup * half, c1 = c0 + half;
-          const int rstride = (int)(((uint32_t)R_THREADS * inv_half) >> 20);  // row groups per pass
+          const int cs = (nx + H_NC - 1) / H_NC;  // column stride = threads per canvas row
+          const uint32_t inv_cs = nx == nx_blk ? (uint32_t)s_pinvh[s] : c_inv20[cs];
+          const int rgroup = (int)(((uint32_t)tid * inv_cs) >> 20);  // tid / cs
+          const int c0 = tid - rgroup * cs;
+          const int rstride = (int)(((uint32_t)R_THREADS * inv_cs) >> 20);  // row groups per pass
           if (rgroup < rstride) {
-            const bool two = c1 < nx;
-            const uint32_t xw0 = s_xwin[tx0 + c0], xw1 = s_xwin[tx0 + (two ? c1 : c0)];
-            const int xmin0 = (int)(int16_t)(xw0 & 0xFFFFu), len0 = (int)((xw0 >> 16) & 0xFFu);
-            const int xmin1 = (int)(int16_t)(xw1 & 0xFFFFu), len1 = (int)((xw1 >> 16) & 0xFFu);
             const uint32_t prefix0 = (uint32_t)__cvta_generic_to_shared(s_prefix);
-            const uint32_t p0 = prefix0 + (xw0 >> 24) * 33u * 4u, p1 = prefix0 + (xw1 >> 24) * 33u * 4u;
-            const int k0 = lds_s32(p0 + ((uint32_t)len0 << 2)), k1 = lds_s32(p1 + ((uint32_t)len1 << 2));
-            const int b0r = bg_r * k0 + (1 << 21), b0g = bg_g * k0 + (1 << 21), b0b = bg_b * k0 + (1 << 21);
-            const int b1r = bg_r * k1 + (1 << 21), b1g = bg_g * k1 + (1 << 21), b1b = bg_b * k1 + (1 << 21);
+            int xmin[H_NC], len[H_NC], kk[H_NC];
+            uint32_t pp[H_NC];
+            bool on[H_NC];
+#pragma unroll
+            for (int q = 0; q < H_NC; ++q) {
+              const int c = c0 + q * cs;
+              on[q] = c < nx;
+              const uint32_t xw = s_xwin[tx0 + (on[q] ? c : c0)];
+              xmin[q] = (int)(int16_t)(xw & 0xFFFFu);
+              len[q] = (int)((xw >> 16) & 0xFFu);
+              pp[q] = prefix0 + (xw >> 24) * 33u * 4u;
+              kk[q] = lds_s32(pp[q] + ((uint32_t)len[q] << 2));  // sum of the window's taps
+            }
             const uint32_t dcol_addr = (uint32_t)__cvta_generic_to_shared(s_dr);
             // raw shared-window addresses, advanced by one row group per iteration
             uint32_t nseg_addr = (uint32_t)__cvta_generic_to_shared(s_nseg) + (uint32_t)(tr0 + rgroup - row_b0);
@@ -607,13 +625,21 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, uint8_t *__restri
             uint32_t ht_addr = (uint32_t)__cvta_generic_to_shared(s_ht) + (uint32_t)(rgroup * TILE_X_MAX + c0) * 4u;
             const uint32_t seg_step = (uint32_t)(rstride * SEGCAP) * 4u;
             const uint32_t ht_step = (uint32_t)(rstride * TILE_X_MAX) * 4u;
-            const uint32_t ht_second = (uint32_t)half * 4u;
+            const uint32_t ht_col = (uint32_t)cs * 4u;
             for (int r = rgroup; r < nr; r += rstride, nseg_addr += rstride, seg_row += seg_step, ht_addr += ht_step) {
               const int nseg = (int)lds_u8(nseg_addr);
-              uint32_t h0 = bg_h, h1 = bg_h;
+              uint32_t hv[H_NC];
+#pragma unroll
+              for (int q = 0; q < H_NC; ++q) hv[q] = bg_h;
               if (nseg) {
                 uint32_t seg_addr = seg_row;
-                int r0 = b0r, g0 = b0g, bl0 = b0b, r1 = b1r, g1 = b1g, bl1 = b1b;
+                int ar[H_NC], ag[H_NC], ab[H_NC];
+#pragma unroll
+                for (int q = 0; q < H_NC; ++q) {
+                  ar[q] = bg_r * kk[q] + (1 << 21);
+                  ag[q] = bg_g * kk[q] + (1 << 21);
+                  ab[q] = bg_b * kk[q] + (1 << 21);
+                }
                 int j = nseg;
 #pragma unroll 1
                 do {
@@ -622,31 +648,45 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, uint8_t *__restri
                   const int xs = (int)(w & 0xFFFu), xe1 = (int)((w >> 12) & 0xFFFu) + 1;
                   const int d = lds_s32(dcol_addr + ((w >> 24) << 2));
                   const int dr = (d << 22) >> 22, dg = (d << 12) >> 22, db = (d << 2) >> 22;
-                  {
-                    const int a = min(max(xs - xmin0, 0), len0), b = min(max(xe1 - xmin0, 0), len0);
-                    const int wt = lds_s32(p0 + ((uint32_t)b << 2)) - lds_s32(p0 + ((uint32_t)a << 2));
-                    r0 += dr * wt; g0 += dg * wt; bl0 += db * wt;
-                  }
-                  {
-                    const int a = min(max(xs - xmin1, 0), len1), b = min(max(xe1 - xmin1, 0), len1);
-                    const int wt = lds_s32(p1 + ((uint32_t)b << 2)) - lds_s32(p1 + ((uint32_t)a << 2));
-                    r1 += dr * wt; g1 += dg * wt; bl1 += db * wt;
+#pragma unroll
+                  for (int q = 0; q < H_NC; ++q) {
+                    const int a = min(max(xs - xmin[q], 0), len[q]), b = min(max(xe1 - xmin[q], 0), len[q]);
+                    const int wt = lds_s32(pp[q] + ((uint32_t)b << 2)) - lds_s32(pp[q] + ((uint32_t)a << 2));
+                    ar[q] += dr * wt; ag[q] += dg * wt; ab[q] += db * wt;
                   }
                 } while (--j);
-                h0 = clip8_q22(r0) | (clip8_q22(g0) << 10) | (clip8_q22(bl0) << 20);
-                h1 = clip8_q22(r1) | (clip8_q22(g1) << 10) | (clip8_q22(bl1) << 20);
+#pragma unroll
+                for (int q = 0; q < H_NC; ++q)
+                  hv[q] = clip8_q22(ar[q]) | (clip8_q22(ag[q]) << 10) | (clip8_q22(ab[q]) << 20);
               }
-              sts_u32(ht_addr, h0);
-              if (two) sts_u32(ht_addr + ht_second, h1);
+#pragma unroll
+              for (int q = 0; q < H_NC; ++q)
+                if (on[q]) sts_u32(ht_addr + (uint32_t)q * ht_col, hv[q]);
             }
           }
         }
         __syncthreads();
         SWB_MARK(8);
-        // ---- V pass: item = (output row ly, column c) ----
-        for (int it = tid; it < ny * nx; it += R_THREADS) {
-          const int ly = (int)(((uint32_t)it * inv_nx) >> 20);
-          const int c = it - ly * nx;
+        // ---- V pass: item = (output row ly, column c).  Consecutive interior rows start 5
+        // canvas rows = 100 words = 4 banks apart in the H tile, so a warp takes 16 columns of
+        // two output rows four apart (16 banks apart): its 32 loads of one tap hit 32 banks.
+        // Rows go in blocks of eight, (j, j + 4); a last block of <= 4 rows pairs (j, j + h);
+        // columns past 16 (at most four) go as warps of 8 rows x 4 columns ----
+        const int nb8 = ny >> 3, m8 = ny & 7;
+        const int hstep = m8 > 4 ? 4 : ((m8 + 1) >> 1);
+        const int n_pair = 4 * nb8 + hstep;
+        const int n_chunk = n_pair + (nx > 16 ? ((ny + 7) >> 3) : 0);
+        for (int chunk = warp; chunk < n_chunk; chunk += NWARP) {
+          int ly, c;
+          if (chunk < n_pair) {
+            const int blk = chunk >> 2;
+            ly = (blk << 3) + (chunk & 3) + ((lane >> 4) ? (blk < nb8 ? 4 : hstep) : 0);
+            c = lane & 15;
+          } else {
+            ly = ((chunk - n_pair) << 3) + (lane >> 2);
+            c = 16 + (lane & 3);
+          }
+          if (ly >= ny || c >= nx) continue;
           const int yo = ty0 + ly;
           const uint32_t yw = s_ywin[yo - yo_b0];
           const int rbase = (int)(int16_t)(yw & 0xFFFFu) - tr0;
@@ -707,8 +747,9 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, uint8_t *__restri
   const int row_bytes = rd.W * 3;
   if ((row_bytes & 15) == 0) {
     const int vec_per_row = row_bytes >> 4;
-    const uint32_t inv_vpr = (1u << 20) / (uint32_t)vec_per_row + 1u;  // i / vec_per_row for i < 2^20 / vpr
-    const bool fast = n_yo * vec_per_row < (1 << 20) / vec_per_row;
+    // i / vec_per_row by reciprocal when the table covers it (i * inv stays below 2^32)
+    const bool fast = vec_per_row <= 64 && n_yo * vec_per_row * vec_per_row < (1 << 20);
+    const uint32_t inv_vpr = fast ? c_inv20[vec_per_row] : 0u;
     for (int i = tid; i < n_yo * vec_per_row; i += R_THREADS) {
       const int ly = fast ? (int)(((uint32_t)i * inv_vpr) >> 20) : i / vec_per_row;
       const int v = i - ly * vec_per_row;
