@@ -154,6 +154,9 @@ def main():
   ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
   ap.add_argument('--workload', default='c2', choices=['c2', 'c3', 'c4', 'c5'])
   ap.add_argument('--envs', type=int, default=0, help='override envs per GPU')
+  ap.add_argument('--gather', default='peer', choices=['peer', 'nccl'],
+                  help='N>1 frame gather: stores into peer memory from the render kernel, or a '
+                       'separate NCCL all-gather')
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--no-e2e', action='store_true')
   args = ap.parse_args()
@@ -184,9 +187,14 @@ def main():
   # frame ring larger than L2 (126 MB) so that every step's frame writes reach HBM
   n_ring = max(2, int(np.ceil(160e6 / frame_bytes)) + 1)
   ring = [raster.new_frames() for _ in range(n_ring)]
-  gathered, inflight = None, []   # inflight: (work handle, ring slot read, gather buffer written)
-  if world > 1:   # double-buffered destination of the per-step frame gather
+  gathered, peer, inflight, n_gslots = None, None, [], 2   # inflight: (work handle, ring slot read, gather slot)
+  if world > 1 and args.gather == 'nccl':   # double-buffered destination of the per-step all-gather
     gathered = [torch.empty((world * E, H, W, 3), dtype=torch.uint8, device=dev) for _ in range(2)]
+  elif world > 1:
+    from spriteworld_b200 import distributed
+    # as many gathered buffers as make one pass over them larger than L2
+    n_gslots = max(2, int(np.ceil(160e6 / (world * frame_bytes))) + 1)
+    peer = distributed.PeerFrames(E, (H, W, 3), dev, n_slots=n_gslots)
 
   def wait_for(pred):
     for item in list(inflight):
@@ -195,13 +203,21 @@ def main():
         inflight.remove(item)
 
   def one_step(t, gather=True):
-    slot, dst = t % n_ring, t % 2
+    slot, dst = t % n_ring, t % (n_gslots if peer is not None else 2)
+    if world > 1 and gather and peer is not None:
+      # the single collective of the path, fused: the render kernel stores each frame into
+      # every rank's gathered buffer over NVLink; a one-element all-reduce on NCCL's stream
+      # is the completion barrier and overlaps the next step
+      wait_for(lambda it: it[2] == dst)      # everyone is done with the step that last used dst
+      eng.step_gather(actions[t % T], raster, peer.slot(dst))
+      inflight.append((peer.barrier(async_op=True), -1, dst))
+      return
     wait_for(lambda it: it[1] == slot)     # the gather that last read this ring buffer
     fr = ring[slot]
     eng.step(actions[t % T], raster, fr)
     if world > 1 and gather:
-      # the single collective of the path: gather the rendered frames of every rank.  It
-      # runs on NCCL's stream and overlaps the next step's compute.
+      # the single collective of the path as a separate NCCL all-gather.  It runs on NCCL's
+      # stream and overlaps the next step's compute.
       wait_for(lambda it: it[2] == dst)
       inflight.append((dist.all_gather_into_tensor(gathered[dst], fr, async_op=True), slot, dst))
 
@@ -330,7 +346,11 @@ def main():
                   max_episode_length=wl.max_episode_length, auto_reset='pooled scenes',
                   pool_depth=K, l2='frame ring of %d buffers (%.0f MB) > L2, no flush'
                   % (n_ring, n_ring * frame_bytes / 1e6),
-                  collective='all_gather of frames per step (async, overlaps the next step)' if world > 1 else 'none'),
+                  collective=('none' if world == 1 else
+                              'frames stored into every rank\'s gathered buffer by the render kernel '
+                              '(NVLink peer memory) + one-element NCCL all-reduce as completion barrier'
+                              if peer is not None else
+                              'NCCL all_gather of frames per step (async, overlaps the next step)')),
       roofline=dict(bound='hbm', achieved=achieved, peak=peak, unit='GB/s',
                     frac=achieved / peak, traffic=traffic, peak_kind=peak_kind,
                     kernel='render_kernel', kernel_ms=render_ms,

@@ -417,8 +417,9 @@ void swb_raster_destroy(swb_raster *r) {
   delete r;
 }
 
-static int launch_render(swb_engine *eng, swb_raster *r, uint8_t *frames, uint8_t *status,
-                         cudaStream_t stream, int env_base = 0, int env_count = -1) {
+static int launch_render_targets(swb_engine *eng, swb_raster *r, const RenderTargets &targets,
+                                 uint8_t *status, cudaStream_t stream, int env_base = 0,
+                                 int env_count = -1) {
   if (r->eng != eng) return fail("raster belongs to another engine");
   RasterDev rd = r->rd;
   rd.max_spans = eng->max_spans;
@@ -432,16 +433,26 @@ static int launch_render(swb_engine *eng, swb_raster *r, uint8_t *frames, uint8_
   if (L.total > max_smem)
     return fail("render needs %d B of shared memory per CTA (limit %d): too many sprite slots / too large a canvas",
                 L.total, max_smem);
-  CUDA_TRY(cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+  auto kernel = targets.n > 1 ? render_kernel<true> : render_kernel<false>;
+  CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
   DevState st = eng->st;
   st.render_status = status;
   if (env_count < 0) env_count = eng->st.E - env_base;
   if (env_count <= 0) return 0;
   dim3 grid(env_count, rd.n_bands);
-  render_kernel<<<grid, R_THREADS, L.total, stream>>>(st, rd, L, frames, env_base);
+  kernel<<<grid, R_THREADS, L.total, stream>>>(st, rd, L, targets, env_base);
   eng->launches++;
   CUDA_TRY(cudaGetLastError());
   return 0;
+}
+
+static int launch_render(swb_engine *eng, swb_raster *r, uint8_t *frames, uint8_t *status,
+                         cudaStream_t stream, int env_base = 0, int env_count = -1) {
+  RenderTargets targets{};
+  targets.dst[0] = frames;
+  targets.n = 1;
+  targets.env_offset = 0;
+  return launch_render_targets(eng, r, targets, status, stream, env_base, env_count);
 }
 
 int swb_render(swb_engine *eng, swb_raster *r, uint8_t *frames, void *stream_) {
@@ -457,6 +468,63 @@ int swb_step_render(swb_engine *eng, swb_raster *r, const void *actions, int32_t
   if (!r || !frames) return fail("swb_step_render: null argument");
   if (swb_step(eng, actions, action_dtype, out, stream_)) return 1;
   return launch_render(eng, r, frames, out->status, static_cast<cudaStream_t>(stream_));
+}
+
+int swb_step_render_gather(swb_engine *eng, swb_raster *r, const void *actions,
+                           int32_t action_dtype, const swb_step_out *out, uint8_t *const *dst,
+                           int32_t n_dst, int64_t env_offset, void *stream_) {
+  if (!r || !dst) return fail("swb_step_render_gather: null argument");
+  if (n_dst < 1 || n_dst > SWB_MAX_PEERS)
+    return fail("swb_step_render_gather: n_dst = %d, expected 1..%d", n_dst, SWB_MAX_PEERS);
+  if (env_offset < 0 || env_offset > INT32_MAX - (eng ? eng->st.E : 0))
+    return fail("swb_step_render_gather: env_offset out of range");
+  RenderTargets targets{};
+  for (int i = 0; i < n_dst; ++i) {
+    if (!dst[i]) return fail("swb_step_render_gather: dst[%d] is null", i);
+    targets.dst[i] = dst[i];
+  }
+  targets.n = n_dst;
+  targets.env_offset = (int)env_offset;
+  if (swb_step(eng, actions, action_dtype, out, stream_)) return 1;
+  return launch_render_targets(eng, r, targets, out->status, static_cast<cudaStream_t>(stream_));
+}
+
+int swb_ipc_alloc(int32_t device, uint64_t bytes, void **ptr, uint8_t *handle) {
+  if (!ptr || !handle || !bytes) return fail("swb_ipc_alloc: bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == SWB_IPC_HANDLE_BYTES, "IPC handle size");
+  CUDA_TRY(cudaSetDevice(device));
+  void *p = nullptr;
+  CUDA_TRY(cudaMalloc(&p, bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t err = cudaIpcGetMemHandle(&h, p);
+  if (err != cudaSuccess) {
+    cudaFree(p);
+    return fail("cudaIpcGetMemHandle: %s", cudaGetErrorString(err));
+  }
+  memcpy(handle, &h, sizeof(h));
+  *ptr = p;
+  return 0;
+}
+
+int swb_ipc_free(void *ptr) {
+  if (ptr) CUDA_TRY(cudaFree(ptr));
+  return 0;
+}
+
+int swb_ipc_open(int32_t device, const uint8_t *handle, void **ptr) {
+  if (!ptr || !handle) return fail("swb_ipc_open: null argument");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  void *p = nullptr;
+  CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  *ptr = p;
+  return 0;
+}
+
+int swb_ipc_close(void *ptr) {
+  if (ptr) CUDA_TRY(cudaIpcCloseMemHandle(ptr));
+  return 0;
 }
 
 int swb_step_host(swb_engine *eng, swb_raster *r, const void *actions, int32_t action_dtype,

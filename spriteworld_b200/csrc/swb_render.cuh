@@ -43,6 +43,15 @@ constexpr int MAX_ROW_SPANS = 12;
 constexpr int EV = SWB_MAX_VERTS;  // edge slots per sprite
 static_assert(EV == 32, "phase A maps one lane to one vertex / edge");
 
+// Where a frame goes.  Normally one buffer; with the frame gather fused into the kernel
+// (swb_step_render_gather) one buffer per rank, each an [n_ranks * E] frame array reached
+// over NVLink peer memory, written at env index env_offset + e.
+struct RenderTargets {
+  uint8_t *dst[SWB_MAX_PEERS];
+  int n;
+  int env_offset;
+};
+
 struct RenderLayout {
   int S, rows, M, band_rows, W, aa, ncx, ncy, cap;
   int off_meta, off_edge_i, off_edge_f, off_edge_yr, off_hl, off_region;
@@ -163,8 +172,9 @@ __device__ unsigned long long g_phase_clk[16];
 #define SWB_MARK(id) do { } while (0)
 #endif
 
+template <bool kPeers>  // kPeers: also store the frame into the other ranks' buffers
 __global__ void __launch_bounds__(R_THREADS)
-render_kernel(DevState st, RasterDev rd, const RenderLayout L, uint8_t *__restrict__ frames,
+render_kernel(DevState st, RasterDev rd, const RenderLayout L, const RenderTargets targets,
               int env_base) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int e = env_base + blockIdx.x;  // frames is indexed by the absolute env id
@@ -742,8 +752,10 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, uint8_t *__restri
     }
   }
 
-  // ---- phase D: staged frame -> HBM, rows flipped (np.flipud) ------------------------
-  uint8_t *dst_frame = frames + (size_t)e * rd.H * rd.W * 3;
+  // ---- phase D: staged frame -> HBM, rows flipped (np.flipud).  With several targets the
+  // same 128-bit values also go to the peers' buffers: the frame gather of the multi-GPU
+  // path rides on the stores of the kernel that produced the frame ------------------------
+  const size_t frame_off = (size_t)(targets.env_offset + e) * rd.H * rd.W * 3;
   const int row_bytes = rd.W * 3;
   if ((row_bytes & 15) == 0) {
     const int vec_per_row = row_bytes >> 4;
@@ -754,13 +766,21 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, uint8_t *__restri
       const int ly = fast ? (int)(((uint32_t)i * inv_vpr) >> 20) : i / vec_per_row;
       const int v = i - ly * vec_per_row;
       const uint4 val = reinterpret_cast<const uint4 *>(s_frame + (size_t)ly * row_bytes)[v];
-      const int out_row = rd.H - 1 - (yo_b0 + ly);
-      reinterpret_cast<uint4 *>(dst_frame + (size_t)out_row * row_bytes)[v] = val;
+      const size_t off = frame_off + (size_t)(rd.H - 1 - (yo_b0 + ly)) * row_bytes + ((size_t)v << 4);
+      *reinterpret_cast<uint4 *>(targets.dst[0] + off) = val;
+      if (kPeers) {
+#pragma unroll 1
+        for (int t = 1; t < targets.n; ++t) *reinterpret_cast<uint4 *>(targets.dst[t] + off) = val;
+      }
     }
   } else {
     for (int i = tid; i < n_yo * row_bytes; i += R_THREADS) {
       const int ly = i / row_bytes, v = i - ly * row_bytes;
-      dst_frame[(size_t)(rd.H - 1 - (yo_b0 + ly)) * row_bytes + v] = s_frame[(size_t)ly * row_bytes + v];
+      const uint8_t val = s_frame[(size_t)ly * row_bytes + v];
+      const size_t off = frame_off + (size_t)(rd.H - 1 - (yo_b0 + ly)) * row_bytes + v;
+      targets.dst[0][off] = val;
+      if (kPeers)
+        for (int t = 1; t < targets.n; ++t) targets.dst[t][off] = val;
     }
   }
   // several bands of one env may race here, but they all OR in the same bit

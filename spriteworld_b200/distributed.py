@@ -66,3 +66,90 @@ class StepGatherer(object):
     self._gather(self.step_type, step_type)
     self._gather(self.success, success)
     return GatheredStep(self.frames, self.reward, self.step_type, self.success)
+
+
+class PeerFrames(object):
+  """Gathered frame buffers every rank's render kernel stores into over NVLink peer memory.
+
+  The frame gather is the path's one collective.  Instead of running it as a
+  separate NCCL all-gather after the render kernel -- whose copy CTAs then compete with the
+  next step's render for SMs -- each rank maps the other ranks' gathered buffers (CUDA IPC)
+  and the render kernel's write-out phase stores every finished frame into all of them
+  (`swb_step_render_gather`).  What remains of the collective is a completion barrier: a
+  one-element all-reduce enqueued after the kernel, on NCCL; with `host_barrier=True`
+  (tests with several ranks on one device, where NCCL refuses to run) a device
+  synchronise plus a host barrier on the default group.
+
+  `n_slots` buffers are kept so that a consumer can still read step t while step t+1 is
+  being written.
+  """
+
+  def __init__(self, n_envs_per_rank, frame_shape, device, n_slots=2, group=None,
+               host_barrier=False):
+    import ctypes
+    import numpy as np
+    from spriteworld_b200 import _native
+    from spriteworld_b200 import engine as engine_lib
+    self._lib = _native.load()
+    self.group = group
+    self.world = dist.get_world_size(group)
+    self.rank = dist.get_rank(group)
+    if self.world > _native.MAX_PEERS:
+      raise ValueError('PeerFrames supports up to %d ranks' % _native.MAX_PEERS)
+    self.device = torch.device(device)
+    self.host_barrier = host_barrier
+    self.E = int(n_envs_per_rank)
+    self.n_slots = int(n_slots)
+    dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+    shape = (self.world * self.E,) + tuple(frame_shape)
+    nbytes = int(np.prod(shape))
+    # my own buffers, exported
+    self._own, handles = [], []
+    for _ in range(self.n_slots):
+      ptr = ctypes.c_void_p()
+      handle = (ctypes.c_uint8 * _native.IPC_HANDLE_BYTES)()
+      _native.check(self._lib.swb_ipc_alloc(dev_index, nbytes, ctypes.byref(ptr), handle))
+      self._own.append(ptr)
+      handles.append(bytes(handle))
+    everyone = [None] * self.world
+    dist.all_gather_object(everyone, (dev_index, handles), group=group)
+    # the peers' buffers, mapped
+    self._opened = []
+    self._ptrs = []     # per slot: ctypes array of world pointers, rank-ordered
+    for slot in range(self.n_slots):
+      arr = (ctypes.c_void_p * self.world)()
+      for r, (_, hs) in enumerate(everyone):
+        if r == self.rank:
+          arr[r] = self._own[slot].value
+        else:
+          p = ctypes.c_void_p()
+          h = (ctypes.c_uint8 * _native.IPC_HANDLE_BYTES).from_buffer_copy(hs[slot])
+          _native.check(self._lib.swb_ipc_open(dev_index, h, ctypes.byref(p)))
+          self._opened.append(p)
+          arr[r] = p.value
+      self._ptrs.append(arr)
+    self.frames = [torch.as_tensor(engine_lib._DevicePointer(self._own[s].value, shape, '|u1'),
+                                   device=self.device) for s in range(self.n_slots)]
+    self._token = torch.zeros(1, dtype=torch.int32, device=self.device)
+
+  def slot(self, i):
+    """Targets of step i for Engine.step_gather: (pointer list, n, env offset, local view)."""
+    s = i % self.n_slots
+    return self._ptrs[s], self.world, self.rank * self.E, self.frames[s]
+
+  def barrier(self, async_op=False):
+    """After it, the frames every rank stored for the steps enqueued so far are in place."""
+    if self.host_barrier:
+      torch.cuda.synchronize(self.device)
+      dist.barrier(group=self.group)
+      return None
+    return dist.all_reduce(self._token, group=self.group, async_op=async_op)
+
+  def close(self):
+    for p in self._opened:
+      self._lib.swb_ipc_close(p)
+    self._opened = []
+    self.frames = []
+    for p in self._own:
+      self._lib.swb_ipc_free(p)
+    self._own = []

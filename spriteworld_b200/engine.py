@@ -179,6 +179,20 @@ class Engine(object):
           ctypes.c_void_p(frames.data_ptr()), self._stream()))
     return StepResult(self._reward, self._step_type, self._success, self._status, frames)
 
+  def step_gather(self, actions, raster, targets):
+    """Environment.step for every env with the frame gather fused into the render kernel:
+    each finished frame is stored into every rank's gathered buffer (`targets`, a
+    distributed.PeerFrames slot) over NVLink peer memory.  Returns the StepResult with the
+    local rank's gathered tensor as `frames`; it is whole after `targets.barrier()`."""
+    if actions.device != self.device or not actions.is_contiguous():
+      raise ValueError('actions must be a contiguous tensor on %s' % self.device)
+    dt = self._action_dtype(actions)
+    ptrs, n, env_offset, local = targets
+    _native.check(self._lib.swb_step_render_gather(
+        self._h, raster._h, ctypes.c_void_p(actions.data_ptr()), dt, ctypes.byref(self._out),
+        ptrs, n, env_offset, self._stream()))
+    return StepResult(self._reward, self._step_type, self._success, self._status, local)
+
   def render(self, raster, frames=None):
     if frames is None:
       frames = raster.new_frames()

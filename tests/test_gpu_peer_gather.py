@@ -1,0 +1,60 @@
+"""The frame gather fused into the render kernel (swb_step_render_gather + PeerFrames).
+
+Two ranks share cuda:0 (the GPU tier of the test-suite has one device): each maps the other's
+gathered buffer through CUDA IPC and its render kernel stores every frame into both.  NCCL
+refuses two ranks on one device, so the handle exchange and the completion barrier run on
+gloo (PeerFrames(host_barrier=True)); the kernel path is the one bench.py uses at N > 1.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+E, STEPS = 96, 5
+
+
+def _worker(rank, world, port, ret):
+  os.environ['MASTER_ADDR'] = '127.0.0.1'
+  os.environ['MASTER_PORT'] = str(port)
+  dist.init_process_group('gloo', rank=rank, world_size=world)
+  try:
+    from spriteworld_b200 import distributed, workloads
+    torch.cuda.set_device(0)
+    wl = workloads.WORKLOADS['c4']()
+    K = 4
+    eng, raster, _ = workloads.build_engine(wl, E, K, device=0, seed=1000 + rank)
+    twin, twin_raster, _ = workloads.build_engine(wl, E, K, device=0, seed=1000 + rank)
+    acts = torch.from_numpy(wl.sample_actions(np.random.RandomState(7 + rank), STEPS, E)).cuda()
+    peer = distributed.PeerFrames(E, (wl.image_size[1], wl.image_size[0], 3), 'cuda:0',
+                                  n_slots=2, host_barrier=True)
+    ok = True
+    for t in range(STEPS):
+      res = eng.step_gather(acts[t], raster, peer.slot(t))
+      peer.barrier()
+      plain = twin.step(acts[t], twin_raster)                # plain path, same seed
+      mine = plain.frames
+      ok = ok and torch.equal(res.reward, plain.reward) and torch.equal(res.step_type, plain.step_type)
+      torch.cuda.synchronize()
+      # every rank's plain frames, exchanged on the host, are what the buffer must hold
+      parts = [torch.empty((E,) + tuple(mine.shape[1:]), dtype=torch.uint8) for _ in range(world)]
+      dist.all_gather(parts, mine.cpu())
+      ok = ok and torch.equal(res.frames.cpu(), torch.cat(parts))
+      dist.barrier()   # nobody overwrites a slot a peer is still comparing
+    ret[rank] = bool(ok)
+    peer.close()
+  finally:
+    dist.destroy_process_group()
+
+
+def test_peer_store_gather_two_ranks_one_device():
+  world = 2
+  port = 29500 + (os.getpid() + 77) % 2000
+  with mp.Manager() as m:
+    ret = m.dict()
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert dict(ret) == {0: True, 1: True}
