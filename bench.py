@@ -154,7 +154,7 @@ def main():
   ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
   ap.add_argument('--workload', default='c2', choices=['c2', 'c3', 'c4', 'c5'])
   ap.add_argument('--envs', type=int, default=0, help='override envs per GPU')
-  ap.add_argument('--gather', default='peer', choices=['peer', 'nccl'],
+  ap.add_argument('--gather', default='peer', choices=['peer', 'ce', 'nccl'],
                   help='N>1 frame gather: stores into peer memory from the render kernel, or a '
                        'separate NCCL all-gather')
   ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -209,8 +209,13 @@ def main():
       # every rank's gathered buffer over NVLink; a one-element all-reduce on NCCL's stream
       # is the completion barrier and overlaps the next step
       wait_for(lambda it: it[2] == dst)      # everyone is done with the step that last used dst
-      eng.step_gather(actions[t % T], raster, peer.slot(dst))
-      inflight.append((peer.barrier(async_op=True), -1, dst))
+      if args.gather == 'ce':
+        # variant: render into this rank's block, then copy-engine pushes to the peers
+        eng.step(actions[t % T], raster, peer.own_slab(dst))
+        inflight.append((peer.push(dst), -1, dst))
+      else:
+        eng.step_gather(actions[t % T], raster, peer.slot(dst))
+        inflight.append((peer.barrier(async_op=True), -1, dst))
       return
     wait_for(lambda it: it[1] == slot)     # the gather that last read this ring buffer
     fr = ring[slot]
@@ -349,6 +354,9 @@ def main():
                   collective=('none' if world == 1 else
                               'frames stored into every rank\'s gathered buffer by the render kernel '
                               '(NVLink peer memory) + one-element NCCL all-reduce as completion barrier'
+                              if peer is not None and args.gather == 'peer' else
+                              'render into the rank\'s block of the gathered buffer, copy-engine pushes to '
+                              'the peers over NVLink + one-element NCCL all-reduce as completion barrier'
                               if peer is not None else
                               'NCCL all_gather of frames per step (async, overlaps the next step)')),
       roofline=dict(bound='hbm', achieved=achieved, peak=peak, unit='GB/s',

@@ -109,6 +109,7 @@ def load():
   L.swb_ipc_free.argtypes = [vp]
   L.swb_ipc_open.argtypes = [ci, vp, ctypes.POINTER(vp)]
   L.swb_ipc_close.argtypes = [vp]
+  L.swb_peer_copy.argtypes = [vp, vp, ctypes.c_uint64, vp]
   L.swb_state_pointers.argtypes = [vp] + [ctypes.POINTER(vp)] * 5
   L.swb_download_state.argtypes = [vp, vp, vp, vp, vp, vp, vp]
   L.swb_upload_state.argtypes = [vp, vp, vp, vp, vp, vp, vp]
@@ -127,7 +128,7 @@ EXPORTS = (
     'swb_last_error', 'swb_version', 'swb_sizeof_config', 'swb_sizeof_task_node',
     'swb_engine_create', 'swb_engine_destroy', 'swb_upload_scenes', 'swb_request_reset',
     'swb_step', 'swb_eval_task', 'swb_apply_action', 'swb_raster_create', 'swb_raster_destroy', 'swb_render', 'swb_step_render',
-    'swb_step_render_gather', 'swb_ipc_alloc', 'swb_ipc_free', 'swb_ipc_open', 'swb_ipc_close',
+    'swb_step_render_gather', 'swb_ipc_alloc', 'swb_ipc_free', 'swb_ipc_open', 'swb_ipc_close', 'swb_peer_copy',
     'swb_step_host', 'swb_state_pointers', 'swb_download_state', 'swb_upload_state',
     'swb_launch_count')
 

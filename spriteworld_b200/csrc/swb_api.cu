@@ -522,6 +522,12 @@ int swb_ipc_open(int32_t device, const uint8_t *handle, void **ptr) {
   return 0;
 }
 
+int swb_peer_copy(void *dst, const void *src, uint64_t bytes, void *stream) {
+  if (!dst || !src) return fail("swb_peer_copy: null argument");
+  CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
 int swb_ipc_close(void *ptr) {
   if (ptr) CUDA_TRY(cudaIpcCloseMemHandle(ptr));
   return 0;

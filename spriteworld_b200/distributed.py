@@ -131,11 +131,59 @@ class PeerFrames(object):
     self.frames = [torch.as_tensor(engine_lib._DevicePointer(self._own[s].value, shape, '|u1'),
                                    device=self.device) for s in range(self.n_slots)]
     self._token = torch.zeros(1, dtype=torch.int32, device=self.device)
+    # copy-engine variant: one side stream per peer
+    self._slab_bytes = nbytes // self.world
+    self._copy_streams = [torch.cuda.Stream(device=self.device) for _ in range(self.world)]
+    self._sync_stream = torch.cuda.Stream(device=self.device)
+    self._slab_read = [None] * self.n_slots   # event: the pushes that read my slab of slot s
 
   def slot(self, i):
     """Targets of step i for Engine.step_gather: (pointer list, n, env offset, local view)."""
     s = i % self.n_slots
     return self._ptrs[s], self.world, self.rank * self.E, self.frames[s]
+
+  def own_slab(self, i):
+    """This rank's block of gathered buffer i % n_slots: render straight into it, then
+    push().  Waits (on the current stream) for the pushes that last read it."""
+    s = i % self.n_slots
+    if self._slab_read[s] is not None:
+      torch.cuda.current_stream(self.device).wait_event(self._slab_read[s])
+    return self.frames[s][self.rank * self.E:(self.rank + 1) * self.E]
+
+  def push(self, i, async_op=True):
+    """Copy-engine variant of the gather: after the render that filled own_slab(i), one
+    peer-to-peer copy per rank on its own stream (DMA over NVLink, no SM involved), then
+    the completion barrier on a side stream.  The caller's stream is not held up."""
+    import ctypes
+    from spriteworld_b200 import _native
+    s = i % self.n_slots
+    lo, hi = self.rank * self.E, (self.rank + 1) * self.E
+    src = self.frames[s][lo:hi]
+    ready = torch.cuda.Event()
+    ready.record(torch.cuda.current_stream(self.device))
+    done = []
+    for r in range(self.world):
+      if r == self.rank:
+        continue
+      st = self._copy_streams[r]
+      st.wait_event(ready)
+      _native.check(self._lib.swb_peer_copy(
+          ctypes.c_void_p(self._ptrs[s][r] + self.rank * self._slab_bytes),
+          ctypes.c_void_p(src.data_ptr()), self._slab_bytes, ctypes.c_void_p(st.cuda_stream)))
+      ev = torch.cuda.Event()
+      ev.record(st)
+      done.append(ev)
+    for ev in done:
+      self._sync_stream.wait_event(ev)
+    with torch.cuda.stream(self._sync_stream):
+      read = torch.cuda.Event()
+      read.record(self._sync_stream)
+      self._slab_read[s] = read
+      if self.host_barrier:
+        self._sync_stream.synchronize()
+        dist.barrier(group=self.group)
+        return None
+      return dist.all_reduce(self._token, group=self.group, async_op=async_op)
 
   def barrier(self, async_op=False):
     """After it, the frames every rank stored for the steps enqueued so far are in place."""

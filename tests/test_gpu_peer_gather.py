@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 E, STEPS = 96, 5
 
 
-def _worker(rank, world, port, ret):
+def _worker(rank, world, port, mode, ret):
   os.environ['MASTER_ADDR'] = '127.0.0.1'
   os.environ['MASTER_PORT'] = str(port)
   dist.init_process_group('gloo', rank=rank, world_size=world)
@@ -34,8 +34,13 @@ def _worker(rank, world, port, ret):
                                   n_slots=2, host_barrier=True)
     ok = True
     for t in range(STEPS):
-      res = eng.step_gather(acts[t], raster, peer.slot(t))
-      peer.barrier()
+      if mode == 'stores':
+        res = eng.step_gather(acts[t], raster, peer.slot(t))
+        peer.barrier()
+      else:   # copy engines: render into this rank's block, push it to the peer
+        res = eng.step(acts[t], raster, peer.own_slab(t))
+        peer.push(t)
+        res.frames = peer.frames[t % 2]
       plain = twin.step(acts[t], twin_raster)                # plain path, same seed
       mine = plain.frames
       ok = ok and torch.equal(res.reward, plain.reward) and torch.equal(res.step_type, plain.step_type)
@@ -51,10 +56,11 @@ def _worker(rank, world, port, ret):
     dist.destroy_process_group()
 
 
-def test_peer_store_gather_two_ranks_one_device():
+@pytest.mark.parametrize('mode', ['stores', 'copy_engine'])
+def test_peer_gather_two_ranks_one_device(mode):
   world = 2
-  port = 29500 + (os.getpid() + 77) % 2000
+  port = 29500 + (os.getpid() + 77 + len(mode)) % 2000
   with mp.Manager() as m:
     ret = m.dict()
-    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, mode, ret), nprocs=world, join=True)
     assert dict(ret) == {0: True, 1: True}
