@@ -741,7 +741,8 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, const RenderTarge
               ab += (int)(t >> 20) * pk.y;
             }
           }
-          uint8_t *px = s_frame + ((size_t)(yo - yo_b0) * rd.W + tx0 + c) * 3;
+          // staged in destination order: output row yo is row H-1-yo of the frame (np.flipud)
+          uint8_t *px = s_frame + ((size_t)(yo_b1 - 1 - yo) * rd.W + tx0 + c) * 3;
           px[0] = (uint8_t)clip8_q22(ar);
           px[1] = (uint8_t)clip8_q22(ag);
           px[2] = (uint8_t)clip8_q22(ab);
@@ -752,35 +753,35 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, const RenderTarge
     }
   }
 
-  // ---- phase D: staged frame -> HBM, rows flipped (np.flipud).  With several targets the
-  // same 128-bit values also go to the peers' buffers: the frame gather of the multi-GPU
-  // path rides on the stores of the kernel that produced the frame ------------------------
-  const size_t frame_off = (size_t)(targets.env_offset + e) * rd.H * rd.W * 3;
+  // ---- phase D: staged frame -> HBM.  The frame is staged in destination order (rows already
+  // flipped, np.flipud), so the band is one contiguous block: one thread hands it to the
+  // bulk-copy engine (TMA, cp.async.bulk shared -> global), once per target.  With several
+  // targets the same block also goes to the other ranks' buffers over NVLink peer memory:
+  // the frame gather of the multi-GPU path is issued by the kernel that produced the frame
+  // and costs it one instruction per rank -------------------------------------------------
   const int row_bytes = rd.W * 3;
-  if ((row_bytes & 15) == 0) {
-    const int vec_per_row = row_bytes >> 4;
-    // i / vec_per_row by reciprocal when the table covers it (i * inv stays below 2^32)
-    const bool fast = vec_per_row <= 64 && n_yo * vec_per_row * vec_per_row < (1 << 20);
-    const uint32_t inv_vpr = fast ? c_inv20[vec_per_row] : 0u;
-    for (int i = tid; i < n_yo * vec_per_row; i += R_THREADS) {
-      const int ly = fast ? (int)(((uint32_t)i * inv_vpr) >> 20) : i / vec_per_row;
-      const int v = i - ly * vec_per_row;
-      const uint4 val = reinterpret_cast<const uint4 *>(s_frame + (size_t)ly * row_bytes)[v];
-      const size_t off = frame_off + (size_t)(rd.H - 1 - (yo_b0 + ly)) * row_bytes + ((size_t)v << 4);
-      *reinterpret_cast<uint4 *>(targets.dst[0] + off) = val;
-      if (kPeers) {
+  const int n_bytes = n_yo * row_bytes;
+  const size_t band_off = (size_t)(targets.env_offset + e) * rd.H * row_bytes + (size_t)(rd.H - yo_b1) * row_bytes;
+  if ((n_bytes & 15) == 0 && (band_off & 15) == 0) {
+    // the tiles were written through the generic proxy; make them visible to the async proxy
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      const uint32_t src = (uint32_t)__cvta_generic_to_shared(s_frame);
 #pragma unroll 1
-        for (int t = 1; t < targets.n; ++t) *reinterpret_cast<uint4 *>(targets.dst[t] + off) = val;
-      }
+      for (int t = 0; t < (kPeers ? targets.n : 1); ++t)
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                     : : "l"(targets.dst[t] + band_off), "r"(src), "r"(n_bytes) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      // the CTA's shared memory must stay until the engine has read it
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
   } else {
-    for (int i = tid; i < n_yo * row_bytes; i += R_THREADS) {
-      const int ly = i / row_bytes, v = i - ly * row_bytes;
-      const uint8_t val = s_frame[(size_t)ly * row_bytes + v];
-      const size_t off = frame_off + (size_t)(rd.H - 1 - (yo_b0 + ly)) * row_bytes + v;
-      targets.dst[0][off] = val;
+    for (int i = tid; i < n_bytes; i += R_THREADS) {
+      const uint8_t val = s_frame[i];
+      targets.dst[0][band_off + i] = val;
       if (kPeers)
-        for (int t = 1; t < targets.n; ++t) targets.dst[t][off] = val;
+        for (int t = 1; t < targets.n; ++t) targets.dst[t][band_off + i] = val;
     }
   }
   // several bands of one env may race here, but they all OR in the same bit
