@@ -235,11 +235,15 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, const RenderTarge
   if (tid == 0) s_overflow = 0;
   const int cur = st.cursor[e];
   // tables first: their loads overlap the sprite records' dependent loads below
+#pragma unroll 1
   for (int i = tid; i < rd.ncls_x * 33; i += R_THREADS) s_prefix[i] = rd.ax.prefix[i];
+#pragma unroll 1
   for (int i = tid; i < (n_rows + 3) / 4; i += R_THREADS) reinterpret_cast<uint32_t *>(s_nseg)[i] = 0u;
+#pragma unroll 1
   for (int i = tid; i < rd.W; i += R_THREADS)
     s_xwin[i] = (uint32_t)(uint16_t)rd.ax.win_min[i] | ((uint32_t)rd.ax.win_len[i] << 16) |
                 ((uint32_t)rd.ax.win_cls[i] << 24);
+#pragma unroll 1
   for (int i = tid; i < n_yo; i += R_THREADS)
     s_ywin[i] = (uint32_t)(uint16_t)rd.ay.win_min[yo_b0 + i] | ((uint32_t)rd.ay.win_len[yo_b0 + i] << 16) |
                 ((uint32_t)rd.ay.win_cls[yo_b0 + i] << 24);
@@ -571,6 +575,7 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, const RenderTarge
       const uint32_t w = r * 0x01010101u;
       if ((n_bytes & 15) == 0) {
         uint4 *f128 = reinterpret_cast<uint4 *>(s_frame);
+#pragma unroll 1
         for (int i = tid; i < (n_bytes >> 4); i += R_THREADS) f128[i] = make_uint4(w, w, w, w);
       } else {
         uint32_t *f32 = reinterpret_cast<uint32_t *>(s_frame);
