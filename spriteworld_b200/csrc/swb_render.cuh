@@ -56,7 +56,7 @@ struct RenderLayout {
   int S, rows, M, band_rows, W, aa, ncx, ncy, cap;
   int off_meta, off_edge_i, off_edge_f, off_edge_yr, off_hl, off_region;
   int off_nseg, off_segs, off_prefix, off_xwin, off_ywin, off_scratch, off_frame, total;
-  int scratch_bytes, list_rows, segcap;
+  int scratch_bytes, segcap;
   __host__ __device__ RenderLayout(int S_, int rows_, int M_, int band_rows_, int W_, int aa_,
                                    int ncx_, int ncy_)
       : S(S_), rows(rows_), M(M_), band_rows(band_rows_), W(W_), aa(aa_), ncx(ncx_), ncy(ncy_) {
@@ -75,7 +75,6 @@ struct RenderLayout {
     off_prefix = take(ncx * 33 * 4);
     off_xwin = take(W * 4);                // per output column: win_min | len<<16 | cls<<24
     off_ywin = take(band_rows * 4);
-    // scratch: H tile + staged frame; phase B aliases it with the per-row crossing lists
     cap = (M > 1) ? 16 : 8;                // crossings kept per (sprite, row)
     // scratch = H tile + staged frame; phase B aliases it with the per-row crossing lists and
     // spans of a chunk of sprites, so it must hold at least one sprite spanning every row
@@ -87,7 +86,6 @@ struct RenderLayout {
     off_frame = take(frame_bytes);
     scratch_bytes = o - off_scratch;
     total = o;
-    list_rows = scratch_bytes / (cap * 4 + 4);  // upper bound; phase B sizes its chunks itself
   }
 };
 
