@@ -51,6 +51,30 @@ def _load(eng, sprites, filters=(), color_to_rgb=None):
   return batch
 
 
+def _load_for_task(eng, sprites, filters):
+  """Like _load, for task evaluation: needs of a sprite only what the reference's tasks touch,
+  `.position` and -- when the task filters -- `.factors` (tasks.py:126-158,196-205), so the
+  same duck-typed stand-ins work."""
+  n, S = len(sprites), eng.n_slots
+  batch = scene.empty_batch(1, S)
+  for j, s in enumerate(sprites):
+    k = S - n + j
+    pos = np.asarray(s.position)
+    batch['x'][0, k], batch['y'][0, k] = float(pos[0]), float(pos[1])
+    batch['pos_f32'][0, k] = 1 if pos.dtype == np.float32 else 0
+    batch['shape'][0, k] = 1                     # any occupied slot; the task never looks at it
+    batch['m00'][0, k] = batch['m11'][0, k] = 1.0
+    member = 0
+    for bit, f in enumerate(filters):
+      if f.contains(s.factors):
+        member |= 1 << bit
+    batch['member'][0, k] = member
+  eng.upload_scenes(batch, [0], [0])
+  eng.upload_state(pos_x=batch['x'], pos_y=batch['y'], cursor=[0], step_count=[0],
+                   reset_next=[0])
+  return batch
+
+
 def _raise_for_status(status):
   if status & _native.ENV_CLUSTER_LABELS:
     raise ValueError('Number of labels is invalid for the Davies-Bouldin score: clustering '
@@ -69,7 +93,7 @@ def task_value(task, sprites):
   task._filters_static()
   sprites = list(sprites)
   eng = _engine(max(1, len(sprites)), _DUMMY_ACTION, nodes, True)
-  _load(eng, sprites, filters)
+  _load_for_task(eng, sprites, filters)
   _native.check(eng._lib.swb_eval_task(eng._h, eng._out, eng._stream()))
   torch.cuda.synchronize(eng.device)
   _raise_for_status(int(eng._status[0].item()))

@@ -9,6 +9,7 @@ import collections
 import numpy as np
 
 from spriteworld_b200 import constants
+from spriteworld_b200 import sprite as sprite_lib
 from spriteworld_b200._dm_env import specs
 from spriteworld_b200.renderers import abstract_renderer
 
@@ -32,6 +33,8 @@ class SpriteFactors(abstract_renderer.AbstractRenderer):
 
   def __init__(self, factors=('x', 'y', 'shape', 'angle', 'scale', 'c0', 'c1', 'c2', 'x_vel',
                               'y_vel')):
+    if not set(factors).issubset(set(sprite_lib.FACTOR_NAMES)):   # handcrafted.py:41-43
+      raise ValueError('Factors have to belong to {}.'.format(sprite_lib.FACTOR_NAMES))
     self._num_sprites = None
     self._factors = factors
     self._per_object_spec = {f: specs.Array(shape=(), dtype=np.float32) for f in factors}

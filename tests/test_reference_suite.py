@@ -1,0 +1,83 @@
+"""The reference's own test files, run against spriteworld_b200 (CPU tier).
+
+`spriteworld` is aliased to `spriteworld_b200`, so every `from spriteworld import ...` in the
+reference's tests/ resolves to this package, unmodified.  The modules that only touch host code
+(factor distributions, sprite generators, shapes, sprites, handcrafted renderers) run as they
+are; the ones that call tasks, action spaces, the PIL renderer or whole environments need the
+device, so here the engine is replaced by the oracle-backed double (tests/oracle_engine.py):
+what is under test is this package's host layer -- task / action compilation, scene packing,
+the plugin protocol, the config modules -- the device arithmetic has its own parity tests
+(`-m gpu`).  Skipped where /root/reference does not exist (the GPU boxes).
+"""
+import importlib
+import importlib.abc
+import importlib.util
+import os
+import sys
+import unittest
+
+import pytest
+
+REF_TESTS = os.path.join(os.environ.get('SPRITEWORLD_REFERENCE', '/root/reference'), 'tests')
+
+pytestmark = pytest.mark.skipif(not os.path.isdir(REF_TESTS), reason='reference tests not present')
+
+
+class _Alias(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+  """spriteworld[.x.y] -> spriteworld_b200[.x.y]"""
+
+  def find_spec(self, name, path, target=None):
+    if name == 'spriteworld' or name.startswith('spriteworld.'):
+      return importlib.util.spec_from_loader(name, self)
+    return None
+
+  def create_module(self, spec):
+    return importlib.import_module('spriteworld_b200' + spec.name[len('spriteworld'):])
+
+  def exec_module(self, module):
+    pass
+
+
+@pytest.fixture
+def reference_alias():
+  from oracle.refshim import loader
+  loader._patch_aliases()   # np.cast / mock aliases the reference's tests rely on
+  finder = _Alias()
+  sys.meta_path.insert(0, finder)
+  yield
+  sys.meta_path.remove(finder)
+  for name in [n for n in sys.modules if n == 'spriteworld' or n.startswith('spriteworld.')]:
+    del sys.modules[name]
+
+
+def _run(rel):
+  path = os.path.join(REF_TESTS, rel + '.py')
+  spec = importlib.util.spec_from_file_location('reference_' + rel.replace('/', '_'), path)
+  mod = importlib.util.module_from_spec(spec)
+  spec.loader.exec_module(mod)
+  suite = unittest.defaultTestLoader.loadTestsFromModule(mod)
+  result = unittest.TestResult()
+  suite.run(result)
+  problems = ['%s: %s' % (t.id(), tb.strip().splitlines()[-1]) for t, tb in
+              result.failures + result.errors]
+  return result.testsRun, problems
+
+
+@pytest.mark.parametrize('rel,n_tests', [
+    ('factor_distributions_test', 39), ('sprite_generators_test', 7), ('shapes_test', 21),
+    ('sprite_test', 16), ('renderers/handcrafted_test', 24)])
+def test_reference_host_tests(reference_alias, rel, n_tests):
+  ran, problems = _run(rel)
+  assert not problems, '\n'.join(problems)
+  assert ran == n_tests
+
+
+@pytest.mark.parametrize('rel,n_tests', [
+    ('tasks_test', 85), ('action_spaces_test', 30), ('renderers/pil_renderer_test', 5),
+    ('configs/configs_test', None)])
+def test_reference_protocol_tests_on_oracle_engine(reference_alias, monkeypatch, rel, n_tests):
+  from tests import oracle_engine
+  oracle_engine.install(monkeypatch)
+  ran, problems = _run(rel)
+  assert not problems, '\n'.join(problems)
+  assert ran == n_tests if n_tests else ran > 0
