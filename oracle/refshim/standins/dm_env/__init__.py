@@ -54,6 +54,14 @@ class Environment(abc.ABC):
   def action_spec(self):
     pass
 
+  def reward_spec(self):
+    from dm_env import specs
+    return specs.Array(shape=(), dtype=float, name='reward')
+
+  def discount_spec(self):
+    from dm_env import specs
+    return specs.BoundedArray(shape=(), dtype=float, minimum=0., maximum=1., name='discount')
+
   def close(self):
     pass
 

@@ -28,8 +28,9 @@ class _MiniSpaces(object):
     def __init__(self, low, high, shape=None, dtype=np.float32):
       self.dtype = np.dtype(dtype)
       self.shape = tuple(shape) if shape is not None else np.shape(low)
-      self.low = np.broadcast_to(np.asarray(low, self.dtype), self.shape)
-      self.high = np.broadcast_to(np.asarray(high, self.dtype), self.shape)
+      with np.errstate(invalid='ignore'):   # infinite bounds of integer boxes, as gym allows
+        self.low = np.broadcast_to(np.asarray(low).astype(self.dtype), self.shape)
+        self.high = np.broadcast_to(np.asarray(high).astype(self.dtype), self.shape)
 
     def sample(self):
       return np.random.uniform(self.low, self.high).astype(self.dtype)
@@ -37,6 +38,13 @@ class _MiniSpaces(object):
     def contains(self, x):
       x = np.asarray(x)
       return x.shape == self.shape and bool(np.all(x >= self.low) and np.all(x <= self.high))
+
+    def __eq__(self, other):
+      return (isinstance(other, type(self)) and self.shape == other.shape and
+              self.dtype == other.dtype and np.array_equal(self.low, other.low) and
+              np.array_equal(self.high, other.high))
+
+    __hash__ = None
 
   class Discrete(object):
 
@@ -50,6 +58,11 @@ class _MiniSpaces(object):
 
     def contains(self, x):
       return 0 <= int(x) < self.n
+
+    def __eq__(self, other):
+      return isinstance(other, type(self)) and self.n == other.n
+
+    __hash__ = None
 
   class Dict(dict):
 
@@ -92,7 +105,10 @@ def _spec_to_space(spec):
 
 
 class GymWrapper(object):
-  """gym.Env-like view of a dm_env style Environment."""
+  """gym.Env-like view of a dm_env style Environment (gym_wrapper.py:42-135).
+
+  Observations are a dict with the keys of the environment's `renderers`; rendering always
+  happens, so render() only returns the last 'image' observation."""
   metadata = {'render.modes': ['rgb_array']}
 
   def __init__(self, env):
@@ -100,12 +116,24 @@ class GymWrapper(object):
     self._last_render = None
     self._action_space = None
     self._observation_space = None
-    self._env.observation_spec()   # forces the renderers to initialise
+    # like the reference (:57-58): a reset sets up the observation specs -- and draws one
+    # scene from init_sprites, which a seeded run must not skip
+    self._env.reset()
+
+  def __getattr__(self, name):
+    return getattr(self._env, name)
 
   @property
   def observation_space(self):
     if self._observation_space is None:
-      self._observation_space = _spec_to_space(self._env.observation_spec())
+      spaces = _spaces()
+      components = {}
+      for key, value in self._env.observation_spec().items():
+        if hasattr(value, 'shape'):   # :67-68, whatever the dtype
+          components[key] = spaces.Box(-np.inf, np.inf, value.shape, dtype=value.dtype)
+        else:                          # per-sprite factor lists: no counterpart in the reference
+          components[key] = _spec_to_space(value)
+      self._observation_space = spaces.Dict(components)
     return self._observation_space
 
   @property
@@ -115,32 +143,25 @@ class GymWrapper(object):
     return self._action_space
 
   def _process_obs(self, obs):
-    out = {}
     for k, v in obs.items():
-      v = np.asarray(v)
-      if v.dtype == bool:
-        v = v.astype(np.float32)
-      out[k] = v
-    if 'image' in out:
-      self._last_render = out['image']
-    return out
+      obs[k] = np.asarray(v)
+      if obs[k].dtype == bool:       # boolean 'success' becomes float32 (:83-85)
+        obs[k] = obs[k].astype(np.float32)
+      if k == 'image':
+        self._last_render = obs[k]
+    return obs
 
   def step(self, action):
+    """-> (obs dict, reward, done, {'discount': ...}) (:91-110)."""
     ts = self._env.step(action)
     obs = self._process_obs(ts.observation)
-    reward = ts.reward or 0
-    if ts.first():      # auto-reset happened: the step's action was ignored
-      reward = 0
-    return obs, reward, ts.last(), {'discount': ts.discount}
+    return obs, ts.reward or 0, ts.last(), {'discount': ts.discount}
 
   def reset(self):
     return self._process_obs(self._env.reset().observation)
 
   def render(self, mode='rgb_array'):
-    if mode != 'rgb_array':
-      raise ValueError("Only render mode 'rgb_array' is supported.")
-    if self._last_render is None:
-      raise ValueError('Environment not started, or has no renderer named "image".')
+    del mode   # always the last RGB observation (:123-133)
     return self._last_render
 
   def close(self):

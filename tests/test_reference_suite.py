@@ -38,14 +38,50 @@ class _Alias(importlib.abc.MetaPathFinder, importlib.abc.Loader):
     pass
 
 
+def _third_party_stand_ins():
+  """dm_env (with test_utils) and gym are absent from this image.  The reference's tests get
+  them as views of what the package itself uses in their place: its dm_env surface
+  (spriteworld_b200._dm_env), its minimal gym spaces, and a restatement of dm_env's
+  EnvironmentTestMixin (oracle/refshim/standins/dm_env/test_utils.py)."""
+  import types
+  from oracle.refshim import loader
+  from spriteworld_b200 import _dm_env, gym_wrapper
+  mods = {}
+  if importlib.util.find_spec('dm_env') is None:
+    dm = types.ModuleType('dm_env')
+    for name in ('Environment', 'TimeStep', 'StepType', 'restart', 'transition', 'termination'):
+      setattr(dm, name, getattr(_dm_env, name))
+    specs = types.ModuleType('dm_env.specs')
+    for name in ('Array', 'BoundedArray', 'DiscreteArray'):
+      setattr(specs, name, getattr(_dm_env.specs, name))
+    spec = importlib.util.spec_from_file_location(
+        'dm_env.test_utils', os.path.join(loader._STANDINS, 'dm_env', 'test_utils.py'))
+    test_utils = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(test_utils)
+    dm.specs, dm.test_utils = specs, test_utils
+    mods.update({'dm_env': dm, 'dm_env.specs': specs, 'dm_env.test_utils': test_utils})
+  if importlib.util.find_spec('gym') is None and importlib.util.find_spec('gymnasium') is None:
+    gym = types.ModuleType('gym')
+    spaces = types.ModuleType('gym.spaces')
+    for name in ('Box', 'Discrete', 'Dict', 'Tuple'):
+      setattr(spaces, name, getattr(gym_wrapper._MiniSpaces, name))
+    gym.spaces = spaces
+    mods.update({'gym': gym, 'gym.spaces': spaces})
+  return mods
+
+
 @pytest.fixture
 def reference_alias():
   from oracle.refshim import loader
   loader._patch_aliases()   # np.cast / mock aliases the reference's tests rely on
   finder = _Alias()
   sys.meta_path.insert(0, finder)
+  stand_ins = _third_party_stand_ins()
+  sys.modules.update(stand_ins)
   yield
   sys.meta_path.remove(finder)
+  for name in stand_ins:
+    sys.modules.pop(name, None)
   for name in [n for n in sys.modules if n == 'spriteworld' or n.startswith('spriteworld.')]:
     del sys.modules[name]
 
@@ -74,7 +110,7 @@ def test_reference_host_tests(reference_alias, rel, n_tests):
 
 @pytest.mark.parametrize('rel,n_tests', [
     ('tasks_test', 85), ('action_spaces_test', 30), ('renderers/pil_renderer_test', 5),
-    ('configs/configs_test', None)])
+    ('configs/configs_test', None), ('environment_test', None), ('gym_wrapper_test', 2)])
 def test_reference_protocol_tests_on_oracle_engine(reference_alias, monkeypatch, rel, n_tests):
   from tests import oracle_engine
   oracle_engine.install(monkeypatch)
