@@ -110,10 +110,10 @@ def test_reference_host_tests(reference_alias, rel, n_tests):
 
 @pytest.mark.parametrize('rel,n_tests', [
     ('tasks_test', 85), ('action_spaces_test', 30), ('renderers/pil_renderer_test', 5),
-    ('configs/configs_test', None), ('environment_test', None), ('gym_wrapper_test', 2)])
+    ('configs/configs_test', 8), ('environment_test', 7), ('gym_wrapper_test', 2)])
 def test_reference_protocol_tests_on_oracle_engine(reference_alias, monkeypatch, rel, n_tests):
   from tests import oracle_engine
   oracle_engine.install(monkeypatch)
   ran, problems = _run(rel)
   assert not problems, '\n'.join(problems)
-  assert ran == n_tests if n_tests else ran > 0
+  assert ran == n_tests
