@@ -191,10 +191,16 @@ def main():
   if world > 1 and args.gather == 'nccl':   # double-buffered destination of the per-step all-gather
     gathered = [torch.empty((world * E, H, W, 3), dtype=torch.uint8, device=dev) for _ in range(2)]
   elif world > 1:
-    from spriteworld_b200 import distributed
+    from spriteworld_b200 import _native, distributed
     # as many gathered buffers as make one pass over them larger than L2
     n_gslots = max(2, int(np.ceil(160e6 / (world * frame_bytes))) + 1)
-    peer = distributed.PeerFrames(E, (H, W, 3), dev, n_slots=n_gslots)
+    try:
+      peer = distributed.PeerFrames(E, (H, W, 3), dev, n_slots=n_gslots)
+    except _native.NativeError as ex:   # raised on every rank or on none
+      if rank == 0:
+        sys.stderr.write('peer-memory gather unavailable (%s); using the NCCL all-gather\n' % ex)
+      args.gather = 'nccl'
+      gathered = [torch.empty((world * E, H, W, 3), dtype=torch.uint8, device=dev) for _ in range(2)]
 
   def wait_for(pred):
     for item in list(inflight):

@@ -68,6 +68,11 @@ class StepGatherer(object):
     return GatheredStep(self.frames, self.reward, self.step_type, self.success)
 
 
+def _native_error(msg):
+  from spriteworld_b200 import _native
+  return _native.NativeError('PeerFrames: ' + msg)
+
+
 class PeerFrames(object):
   """Gathered frame buffers every rank's render kernel stores into over NVLink peer memory.
 
@@ -103,31 +108,40 @@ class PeerFrames(object):
     dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
     shape = (self.world * self.E,) + tuple(frame_shape)
     nbytes = int(np.prod(shape))
-    # my own buffers, exported
-    self._own, handles = [], []
-    for _ in range(self.n_slots):
-      ptr = ctypes.c_void_p()
-      handle = (ctypes.c_uint8 * _native.IPC_HANDLE_BYTES)()
-      _native.check(self._lib.swb_ipc_alloc(dev_index, nbytes, ctypes.byref(ptr), handle))
-      self._own.append(ptr)
-      handles.append(bytes(handle))
+    # my own buffers, exported.  Failures are agreed on by all ranks (a rank that raised
+    # alone would leave the others waiting in the next collective).
+    self._own, self._opened, self._ptrs, handles, error = [], [], [], [], None
+    try:
+      for _ in range(self.n_slots):
+        ptr = ctypes.c_void_p()
+        handle = (ctypes.c_uint8 * _native.IPC_HANDLE_BYTES)()
+        _native.check(self._lib.swb_ipc_alloc(dev_index, nbytes, ctypes.byref(ptr), handle))
+        self._own.append(ptr)
+        handles.append(bytes(handle))
+    except _native.NativeError as ex:
+      error = 'rank %d: %s' % (self.rank, ex)
     everyone = [None] * self.world
-    dist.all_gather_object(everyone, (dev_index, handles), group=group)
-    # the peers' buffers, mapped
-    self._opened = []
-    self._ptrs = []     # per slot: ctypes array of world pointers, rank-ordered
-    for slot in range(self.n_slots):
-      arr = (ctypes.c_void_p * self.world)()
-      for r, (_, hs) in enumerate(everyone):
-        if r == self.rank:
-          arr[r] = self._own[slot].value
-        else:
-          p = ctypes.c_void_p()
-          h = (ctypes.c_uint8 * _native.IPC_HANDLE_BYTES).from_buffer_copy(hs[slot])
-          _native.check(self._lib.swb_ipc_open(dev_index, h, ctypes.byref(p)))
-          self._opened.append(p)
-          arr[r] = p.value
-      self._ptrs.append(arr)
+    dist.all_gather_object(everyone, (error, handles), group=group)
+    self._agree([e for e, _ in everyone])
+    # the peers' buffers, mapped (per slot: ctypes array of world pointers, rank-ordered)
+    try:
+      for slot in range(self.n_slots):
+        arr = (ctypes.c_void_p * self.world)()
+        for r, (_, hs) in enumerate(everyone):
+          if r == self.rank:
+            arr[r] = self._own[slot].value
+          else:
+            p = ctypes.c_void_p()
+            h = (ctypes.c_uint8 * _native.IPC_HANDLE_BYTES).from_buffer_copy(hs[slot])
+            _native.check(self._lib.swb_ipc_open(dev_index, h, ctypes.byref(p)))
+            self._opened.append(p)
+            arr[r] = p.value
+        self._ptrs.append(arr)
+    except _native.NativeError as ex:
+      error = 'rank %d: %s' % (self.rank, ex)
+    errors = [None] * self.world
+    dist.all_gather_object(errors, error, group=group)
+    self._agree(errors)
     self.frames = [torch.as_tensor(engine_lib._DevicePointer(self._own[s].value, shape, '|u1'),
                                    device=self.device) for s in range(self.n_slots)]
     self._token = torch.zeros(1, dtype=torch.int32, device=self.device)
@@ -136,6 +150,12 @@ class PeerFrames(object):
     self._copy_streams = [torch.cuda.Stream(device=self.device) for _ in range(self.world)]
     self._sync_stream = torch.cuda.Stream(device=self.device)
     self._slab_read = [None] * self.n_slots   # event: the pushes that read my slab of slot s
+
+  def _agree(self, errors):
+    errors = [e for e in errors if e]
+    if errors:
+      self.close()
+      raise _native_error('; '.join(errors))
 
   def slot(self, i):
     """Targets of step i for Engine.step_gather: (pointer list, n, env offset, local view)."""
@@ -194,10 +214,10 @@ class PeerFrames(object):
     return dist.all_reduce(self._token, group=self.group, async_op=async_op)
 
   def close(self):
-    for p in self._opened:
+    for p in getattr(self, '_opened', []):
       self._lib.swb_ipc_close(p)
     self._opened = []
     self.frames = []
-    for p in self._own:
+    for p in getattr(self, '_own', []):
       self._lib.swb_ipc_free(p)
     self._own = []
