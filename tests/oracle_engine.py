@@ -142,6 +142,12 @@ class OracleEngine(object):
     return dict(pos_x=bo.cur['x'].copy(), pos_y=bo.cur['y'].copy(), cursor=bo.cursor.copy(),
                 step_count=bo.step_count.copy(), reset_next=bo.reset_next.copy())
 
+  def state_tensors(self):
+    bo = self._bo
+    return dict(pos_x=torch.from_numpy(bo.cur['x'].copy()), pos_y=torch.from_numpy(bo.cur['y'].copy()),
+                cursor=torch.from_numpy(bo.cursor), step_count=torch.from_numpy(bo.step_count),
+                reset_next=torch.from_numpy(bo.reset_next))
+
   def launch_count(self):
     return self._launches
 

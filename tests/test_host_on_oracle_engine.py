@@ -1,0 +1,60 @@
+"""CPU tier: the host layer of the package (drop-in Environment, plugin protocol) driven
+through the oracle-backed engine double (tests/oracle_engine.py).
+
+The bodies are the GPU tests of tests/test_gpu_api.py, unchanged: the same expectations --
+episodes stepped by the reference, tables from the reference's tests -- hold whether the
+device or its CPU restatement executes the step, so a regression in the Python layer (scene
+packing, RNG consumption order, the two-slot scene ring, TimeStep assembly, error mapping)
+shows up here without a GPU.  Device arithmetic itself is not under test in this file.
+"""
+import pytest
+
+from tests import oracle_engine
+from tests import test_gpu_api as gpu_tests
+
+
+@pytest.fixture(autouse=True)
+def _oracle_engine(monkeypatch):
+  oracle_engine.install(monkeypatch)
+
+
+@pytest.mark.parametrize('fixture,config,mode', gpu_tests.DROPIN)
+def test_dropin_environment_reproduces_reference_episode(fixture, config, mode):
+  gpu_tests.test_dropin_environment_reproduces_reference_episode(fixture, config, mode)
+
+
+def test_environment_cadence():
+  gpu_tests.test_environment_cadence()
+
+
+def test_select_move_script():
+  gpu_tests.test_select_move_script()
+
+
+def test_drag_and_drop_script():
+  gpu_tests.test_drag_and_drop_script()
+
+
+@pytest.mark.parametrize('init,action,final,keep', gpu_tests.EMBODIED_CASES)
+def test_embodied_moves(init, action, final, keep):
+  gpu_tests.test_embodied_moves(init, action, final, keep)
+
+
+def test_find_goal_tables():
+  gpu_tests.test_find_goal_tables()
+
+
+def test_clustering_and_meta_tables():
+  gpu_tests.test_clustering_and_meta_tables()
+
+
+def test_pil_renderer_protocol():
+  gpu_tests.test_pil_renderer_protocol()
+
+
+def test_batched_environment_matches_oracle_with_pool_refill():
+  gpu_tests.test_batched_environment_matches_oracle_with_pool_refill()
+
+
+def test_batched_factor_observations_and_gym_surface():
+  gpu_tests.test_batched_factor_observations_and_gym_surface()
