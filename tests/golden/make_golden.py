@@ -13,7 +13,6 @@ Fixtures
   episodes_<cfg>.npz per-env scene pools, action scripts and the per-step outputs of
                      Environment.step (positions, reward, step_type, success, frames)
 """
-import colorsys
 import json
 import os
 import sys

@@ -1,7 +1,6 @@
 """world_size-2 gloo test of the multi-GPU host logic (env sharding + frame gather)."""
 import os
 
-import numpy as np
 import pytest
 import torch
 import torch.distributed as dist
