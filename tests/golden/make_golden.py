@@ -33,7 +33,7 @@ from spriteworld.configs.cobra import (clustering, goal_finding_more_targets,  #
                                        goal_finding_new_position, sorting)
 from spriteworld.configs.examples import goal_finding_clustering, goal_finding_embodied  # noqa
 
-OUT = os.path.dirname(os.path.abspath(__file__))
+OUT = os.environ.get('SWB_GOLDEN_OUT') or os.path.dirname(os.path.abspath(__file__))
 SHAPE_IDS = {name: int(constants.ShapeType[name]) for name in constants.SHAPES}
 
 FIELDS = ('x', 'y', 'pos_f32', 'shape', 'angle', 'scale', 'c0', 'c1', 'c2', 'color_f32',
