@@ -113,9 +113,11 @@ def test_random_scenes_match_oracle():
   shapes, _ = fixtures.render_cases()
   tab = oracle.shape_table(shapes)
   rng = np.random.RandomState(42)
-  E, S = 48, 7
-  for (w, h, aa, bg) in [(64, 64, 5, (0, 0, 0)), (128, 128, 5, (3, 200, 50)), (40, 56, 3, (9, 9, 9)),
-                         (32, 32, 1, (0, 0, 0))]:
+  E = 48
+  # S = 11: more sprites than the render CTA has warps (two sprites share a set-up warp)
+  for (w, h, aa, bg, S) in [(64, 64, 5, (0, 0, 0), 7), (128, 128, 5, (3, 200, 50), 7),
+                            (40, 56, 3, (9, 9, 9), 7), (32, 32, 1, (0, 0, 0), 7),
+                            (64, 64, 5, (0, 0, 0), 11)]:
     arrs = dict(
         x=rng.uniform(-0.1, 1.1, (E, S)).astype(np.float32).astype(np.float64),
         y=rng.uniform(-0.1, 1.1, (E, S)).astype(np.float32).astype(np.float64),
