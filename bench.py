@@ -78,13 +78,24 @@ def usable_cores():
     n = len(os.sched_getaffinity(0))
   except AttributeError:
     n = os.cpu_count() or 1
-  try:
+  quota = None
+  try:   # cgroup v2
     with open('/sys/fs/cgroup/cpu.max') as f:
-      quota, period = f.read().split()[:2]
-    if quota != 'max':
-      n = max(1, min(n, int(round(int(quota) / float(period)))))
+      q, period = f.read().split()[:2]
+    if q != 'max':
+      quota = int(q) / float(period)
   except (OSError, ValueError):
-    pass
+    try:   # cgroup v1
+      with open('/sys/fs/cgroup/cpu/cpu.cfs_quota_us') as f:
+        q = int(f.read())
+      with open('/sys/fs/cgroup/cpu/cpu.cfs_period_us') as f:
+        period = int(f.read())
+      if q > 0 and period > 0:
+        quota = q / float(period)
+    except (OSError, ValueError):
+      pass
+  if quota:
+    n = max(1, min(n, int(round(quota))))
   return n
 
 
