@@ -348,7 +348,14 @@ class BatchedEnvironment(object):
       elif a.dtype != np.float32:
         a = a.astype(np.float64)
       t = torch.from_numpy(np.ascontiguousarray(a))
-    return t.to(dev).contiguous()
+    t = t.to(dev)
+    noise_scale = getattr(self._action_space, '_noise_scale', None)
+    if noise_scale and self._action_space.compile()['kind'] != 'embodied':
+      # SelectMove.apply_noise_to_action (action_spaces.py:69-75), one draw per env; like
+      # there, float32 actions become float64 by the addition
+      noise = self._rng.normal(loc=0.0, scale=noise_scale, size=(self.n_envs, 4))
+      t = t.to(torch.float64) + torch.from_numpy(noise).to(dev)
+    return t.contiguous()
 
   def _timestep(self, res):
     obs = collections.OrderedDict()

@@ -58,3 +58,31 @@ def test_batched_environment_matches_oracle_with_pool_refill():
 
 def test_batched_factor_observations_and_gym_surface():
   gpu_tests.test_batched_factor_observations_and_gym_surface()
+
+
+def test_batched_environment_applies_action_noise():
+  """SelectMove(noise_scale=...) (action_spaces.py:69-75) in the batched environment: same
+  result as feeding pre-noised float64 actions drawn from an identically seeded stream."""
+  import numpy as np
+  from spriteworld_b200 import action_spaces, environment
+  from spriteworld_b200.configs.cobra import goal_finding_more_targets as cfgmod
+
+  def make(noise_scale, seed):
+    cfg = cfgmod.get_config('train')
+    cfg['action_space'] = action_spaces.SelectMove(scale=0.25, noise_scale=noise_scale)
+    return environment.BatchedEnvironment(n_envs=16, pool_depth=6,
+                                          rng=np.random.RandomState(seed), **cfg)
+
+  noisy, plain = make(0.05, 3), make(None, 3)
+  twin = np.random.RandomState(3)
+  twin.set_state(plain._rng.get_state())     # the stream after both sampled their scene pools
+  noisy.reset(); plain.reset()
+  twin.normal(size=(16, 4))                  # reset() stepped once with a dummy action
+  actions = np.random.RandomState(11).uniform(0, 1, (3, 16, 4)).astype(np.float32)
+  for t in range(3):
+    a = noisy.step(actions[t])
+    pre = actions[t] + twin.normal(loc=0.0, scale=0.05, size=(16, 4))
+    b = plain.step(pre)
+    assert np.array_equal(noisy.engine.download_state()['pos_x'], plain.engine.download_state()['pos_x'])
+    assert np.array_equal(a.reward.numpy(), b.reward.numpy())
+    assert np.array_equal(a.observation['image'].numpy(), b.observation['image'].numpy())
