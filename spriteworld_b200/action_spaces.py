@@ -29,6 +29,13 @@ class SelectMove(object):
   def get_motion(self, action):
     return (action[2:] - 0.5) * self._scale
 
+  def get_sprite_from_position(self, position, sprites):
+    """Top-most sprite containing `position`, or None (action_spaces.py:77-81)."""
+    for sprite in sprites[::-1]:
+      if sprite.contains_point(position):
+        return sprite
+    return None
+
   def apply_noise_to_action(self, action):
     """Adds N(0, noise_scale) to the action if noise_scale is set (host side, np.random)."""
     if self._noise_scale:
@@ -78,6 +85,14 @@ class Embodied(object):
 
   def get_non_body_sprites(self, sprites):
     return sprites[:-1]
+
+  def get_carried_sprite(self, sprites):
+    """Top-most non-body sprite under the body's position, or None (action_spaces.py:180-185)."""
+    body_position = self.get_body_sprite(sprites).position
+    for sprite in self.get_non_body_sprites(sprites)[::-1]:
+      if sprite.contains_point(body_position):
+        return sprite
+    return None
 
   def step(self, action, sprites, keep_in_frame):
     if action[1] not in self.action_to_motion:

@@ -156,6 +156,12 @@ class Environment(dm_env.Environment):
   def success(self):
     return self._task.success(self._sprites) if self._last is None else self._last[2]
 
+  def should_terminate(self):
+    """What the device decides each step, evaluated on the host objects (environment.py:83-86)."""
+    timeout = self._step_count >= self._max_episode_length
+    out_of_frame = any(sprite.out_of_frame for sprite in self._sprites)
+    return bool(self.success() or out_of_frame or timeout)
+
   def step(self, action):
     if self._reset_next_step:
       return self.reset()

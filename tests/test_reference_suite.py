@@ -117,3 +117,55 @@ def test_reference_protocol_tests_on_oracle_engine(reference_alias, monkeypatch,
   ran, problems = _run(rel)
   assert not problems, '\n'.join(problems)
   assert ran == n_tests
+
+
+SURFACE_MODULES = [
+    'action_spaces', 'constants', 'environment', 'factor_distributions', 'gym_wrapper', 'shapes',
+    'sprite', 'sprite_generators', 'tasks', 'renderers', 'renderers.abstract_renderer',
+    'renderers.color_maps', 'renderers.handcrafted', 'renderers.pil_renderer',
+    'configs.cobra.common']
+
+
+def test_public_surface_of_the_reference_is_present():
+  """Every public class, function, method and constructor parameter of the reference's modules
+  on and around the path exists under the same name in spriteworld_b200 (demo_ui / run_demo /
+  example_run_loop are out of scope)."""
+  import inspect
+  from oracle.refshim import loader
+  stand_ins = _third_party_stand_ins()
+  sys.modules.update(stand_ins)
+  try:
+    loader.load_reference()
+    missing = []
+    for m in SURFACE_MODULES:
+      ref = importlib.import_module('spriteworld.' + m)
+      ours = importlib.import_module('spriteworld_b200.' + m)
+      for name, obj in vars(ref).items():
+        if name.startswith('_') or inspect.ismodule(obj) or type(obj).__name__ == '_Feature':
+          continue   # private, submodule, `from __future__ import ...`
+        if getattr(obj, '__module__', ref.__name__) != ref.__name__ and (
+            inspect.isclass(obj) or inspect.isfunction(obj)) and m != 'renderers':
+          continue   # imported helper; `renderers` re-exports its classes on purpose
+        if not hasattr(ours, name):
+          missing.append('%s.%s' % (m, name))
+          continue
+        mine = getattr(ours, name)
+        if inspect.isclass(obj):
+          missing += ['%s.%s.%s' % (m, name, a) for a in vars(obj)
+                      if not a.startswith('_') and not hasattr(mine, a)]
+          if '__init__' in vars(obj):
+            want = [p for p in inspect.signature(obj.__init__).parameters if p != 'self']
+            have = [p for p in inspect.signature(mine.__init__).parameters if p != 'self']
+            if want != have[:len(want)]:
+              missing.append('%s.%s(%s)' % (m, name, ', '.join(want)))
+        elif inspect.isfunction(obj):
+          want = list(inspect.signature(obj).parameters)
+          have = list(inspect.signature(mine).parameters)
+          if want != have[:len(want)]:
+            missing.append('%s.%s(%s)' % (m, name, ', '.join(want)))
+    assert not missing, missing
+  finally:
+    for name in stand_ins:
+      sys.modules.pop(name, None)
+    for name in [n for n in sys.modules if n == 'spriteworld' or n.startswith('spriteworld.')]:
+      del sys.modules[name]
