@@ -156,6 +156,9 @@ class Discrete(AbstractDistribution):
 
   def sample_batch(self, n, rng=None):
     index = _rng(rng).choice(len(self.candidates), size=n, p=self.probs)
+    if len(set(type(v) for v in self.candidates)) == 1:
+      # homogeneous candidates: any sample of them types the same way, so type once and index
+      return {self.key: _as_column(list(self.candidates))[index]}
     return {self.key: _as_column([self.candidates[i] for i in index])}
 
   def contains(self, spec):
@@ -164,7 +167,17 @@ class Discrete(AbstractDistribution):
 
   def contains_batch(self, columns):
     self._need(self.key, columns)
-    return np.array([v in self.candidates for v in columns[self.key]], bool)
+    col = columns[self.key]
+    if col.dtype == object and len(col) >= 64:
+      # object columns (shape names): decide once per distinct value; values that do not
+      # order against each other (mixed types) take the plain loop
+      try:
+        values, inverse = np.unique(col, return_inverse=True)
+      except TypeError:
+        values = None
+      if values is not None:
+        return np.array([v in self.candidates for v in values], bool)[inverse.reshape(-1)]
+    return np.array([v in self.candidates for v in col], bool)
 
   def to_str(self, indent):
     return _pad(indent) + '<Discrete: key={}, candidates={}, probs={}>'.format(

@@ -34,20 +34,28 @@ _matrix_cache = {}
 
 
 def transform_matrices(scale, angle):
-  """Vectorised transform_matrix over arrays (values are cached: configs use few)."""
-  scale = np.asarray(scale, dtype=np.float64)
-  angle = np.asarray(angle, dtype=np.float64)
-  out = np.empty(scale.shape + (4,), np.float64)
-  flat_s, flat_a, flat_o = scale.reshape(-1), angle.reshape(-1), out.reshape(-1, 4)
-  for i in range(flat_s.shape[0]):
-    key = (flat_s[i], flat_a[i])
+  """Vectorised transform_matrix over arrays: the scalar function runs once per distinct
+  (scale, angle) bit pattern (configs use few) and the results are scattered back."""
+  scale = np.ascontiguousarray(scale, dtype=np.float64)
+  angle = np.ascontiguousarray(angle, dtype=np.float64)
+  if scale.size == 0:
+    return np.empty(scale.shape + (4,), np.float64)
+  # distinct by bit pattern (0.0 and -0.0 stay apart: they give differently signed zeros);
+  # two 1-D uniques and one over the combined small index are much cheaper than a row-wise one
+  us, inv_s = np.unique(scale.reshape(-1).view(np.int64), return_inverse=True)
+  ua, inv_a = np.unique(angle.reshape(-1).view(np.int64), return_inverse=True)
+  pair_ids, inverse = np.unique(inv_s.reshape(-1) * len(ua) + inv_a.reshape(-1), return_inverse=True)
+  us, ua = us.view(np.float64), ua.view(np.float64)
+  mats = np.empty((pair_ids.shape[0], 4), np.float64)
+  for i, pid in enumerate(pair_ids):
+    key = (us[pid // len(ua)], ua[pid % len(ua)])
     m = _matrix_cache.get(key)
     if m is None:
-      m = transform_matrix(flat_s[i], flat_a[i])
+      m = transform_matrix(key[0], key[1])
       if len(_matrix_cache) < 65536:
         _matrix_cache[key] = m
-    flat_o[i] = m
-  return out
+    mats[i] = m
+  return mats[inverse.reshape(-1)].reshape(scale.shape + (4,))
 
 
 def empty_batch(n_scenes, n_slots):
@@ -85,14 +93,25 @@ _DEFAULTS = dict(x=0.5, y=0.5, shape='square', angle=0, scale=0.1, c0=0, c1=0, c
                  x_vel=0.0, y_vel=0.0)   # Sprite.__init__ defaults (sprite.py:56-66)
 
 
+def _default_column(default, rows):
+  """`rows` copies of a Sprite.__init__ default, typed like factor_distributions._as_column
+  types a list of them: float -> float64, int -> int64, anything else an object column."""
+  if isinstance(default, float):
+    return np.full(rows, default, np.float64)
+  if isinstance(default, int):
+    return np.full(rows, default, np.int64)
+  out = np.empty(rows, dtype=object)
+  out[:] = [default] * rows
+  return out
+
+
 def _full_columns(table):
   """The ten factor columns of a SpriteTable, defaults filled in, typed like
   `Sprite.factors` would type them (positions are float32 only if x and y both are)."""
-  from spriteworld_b200.factor_distributions import _as_column
   cols = {}
   for name, default in _DEFAULTS.items():
     col = table.columns.get(name)
-    cols[name] = _as_column([default] * table.rows) if col is None else col
+    cols[name] = _default_column(default, table.rows) if col is None else col
   x, y = cols['x'], cols['y']
   if not (x.dtype == np.float32 and y.dtype == np.float32):
     # np.array([x, y]) promotes: anything that is not float32 + float32 becomes float64
@@ -119,7 +138,9 @@ def _shape_ids(col):
   from spriteworld_b200 import constants
   if col.dtype != object and np.issubdtype(col.dtype, np.integer):
     return col.astype(np.uint8)
-  return np.array([int(constants.ShapeType[str(v)]) for v in col], np.uint8)
+  names, inverse = np.unique(col.astype(str), return_inverse=True)   # a handful of names
+  ids = np.array([int(constants.ShapeType[str(v)]) for v in names], np.uint8)
+  return ids[inverse.reshape(-1)]
 
 
 def _table_rgb(cols, color_to_rgb):
