@@ -332,7 +332,8 @@ class BatchedEnvironment(object):
     if total <= 0:
       return
     env_ids = np.repeat(np.arange(self.n_envs), n_new)
-    offs = np.concatenate([np.arange(1, n + 1) for n in n_new if n > 0])
+    # 1..n_new[e] for every env, concatenated
+    offs = np.arange(total) - np.repeat(np.cumsum(n_new) - n_new, n_new) + 1
     absolute = np.repeat(self._refilled_upto, n_new) + offs
     layout = self._sample(total)
     self._upload(layout, env_ids, absolute % K)
