@@ -86,3 +86,52 @@ def test_batched_environment_applies_action_noise():
     assert np.array_equal(noisy.engine.download_state()['pos_x'], plain.engine.download_state()['pos_x'])
     assert np.array_equal(a.reward.numpy(), b.reward.numpy())
     assert np.array_equal(a.observation['image'].numpy(), b.observation['image'].numpy())
+
+
+def test_batched_environment_refill_never_serves_a_stale_scene():
+  """The pool refill at the fastest consumption the protocol allows (max_episode_length=1:
+  a scene every two steps).  Every scene an env lands on must have been uploaded for exactly
+  that visit of its ring slot (never a leftover of the previous lap), and the outputs must
+  equal the oracle stepping the same pool."""
+  import numpy as np
+  from oracle import oracle
+  from spriteworld_b200 import constants, environment
+  from spriteworld_b200.configs.cobra import sorting
+  from tests import fixtures
+  cfg = sorting.get_config('train')
+  cfg['max_episode_length'] = 1           # FIRST, LAST, FIRST, ...: a scene every two steps
+  E, K, T = 64, 5, 60
+  env = environment.BatchedEnvironment(n_envs=E, pool_depth=K, rng=np.random.RandomState(5),
+                                       **cfg)
+  eng = env.engine
+  S = eng.n_slots
+  uploads = np.ones((E, K), np.int64)      # the constructor filled every slot once
+  pushed = eng.upload_scenes
+
+  def upload(batch, env_ids, ring_slots):
+    np.add.at(uploads, (np.asarray(env_ids), np.asarray(ring_slots)), 1)
+    return pushed(batch, env_ids, ring_slots)
+
+  eng.upload_scenes = upload
+  # an independent oracle over a live mirror of the pool (the double's own pool array)
+  nodes, _ = cfg['task'].compile()
+  ocfg = fixtures.env_cfg_from_meta(dict(action=cfg['action_space'].compile(), keep_in_frame=True,
+                                         max_episode_length=1, nodes=nodes))
+  bo = oracle.BatchOracle(ocfg, oracle.shape_table(constants.SHAPES), oracle.raster_cfg(64, 64, 5),
+                          eng._bo.pool.copy())
+  bo.pool = eng._bo.pool
+  absolute = np.zeros(E, np.int64)         # index of the scene each env is on
+  last_cursor = np.zeros(E, np.int64)
+  rng = np.random.RandomState(11)
+  for t in range(T):
+    a = rng.uniform(0, 1, (E, 4)).astype(np.float32)
+    ts = env.step(a)
+    bo.step(a)
+    cur = eng._bo.cursor.astype(np.int64)
+    absolute += (cur - last_cursor) % K
+    last_cursor = cur
+    assert np.array_equal(uploads[np.arange(E), absolute % K], absolute // K + 1), t
+    assert np.array_equal(ts.step_type.numpy(), bo.step_type), t
+    assert np.array_equal(ts.observation['image'].numpy(), bo.frames), t
+  assert absolute.min() >= 2 * K           # every ring went round at least twice
+  env.close()
