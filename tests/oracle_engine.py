@@ -97,7 +97,11 @@ class OracleEngine(object):
 
   def upload_scenes(self, scenes, env_ids, ring_slots):
     env_ids, ring_slots = np.asarray(env_ids, np.int64), np.asarray(ring_slots, np.int64)
-    for f in _FIELDS:
+    n, S = len(env_ids), self.n_slots
+    assert len(ring_slots) == n and (ring_slots >= 0).all() and (ring_slots < self.pool_depth).all()
+    for f in _FIELDS:   # the shapes engine.Engine.upload_scenes insists on
+      tail = (3,) if f == 'rgb' else ()
+      assert np.shape(scenes[f]) == (n, S) + tail, (f, np.shape(scenes[f]), (n, S) + tail)
       self._bo.pool[f][env_ids, ring_slots] = scenes[f]
 
   def upload_state(self, pos_x=None, pos_y=None, cursor=None, step_count=None, reset_next=None):
