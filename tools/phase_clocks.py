@@ -17,8 +17,10 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-NAMES = ['0 load+tables', 'A1 vertices', 'A2 edges+plan', 'A3 joins', 'B_pre', 'B1 scan',
-         'B2 fold', 'bg fill', 'C H pass', 'C V pass', 'D store']
+# index = id of the SWB_MARK that ends the phase (ids 0-2 are unused since the set-up phases
+# were fused into one)
+NAMES = ['-', '-', '-', 'A set-up (+tables)', 'B partition', 'B1 scan', 'B2 fold', 'background',
+         'C H pass', 'C V pass', 'D write-out']
 
 
 def main():
@@ -56,6 +58,8 @@ def main():
   L.swb_debug_phase_clocks(out)
   tot = float(sum(out[:11]))
   for i, n in enumerate(NAMES):
+    if n == '-':
+      continue
     print('%-16s %6.2f%%  %8.0f cycles/CTA' % (n, 100.0 * out[i] / tot, out[i] / (args.steps * wl.n_envs)))
   print('total %.0f cycles/CTA' % (tot / (args.steps * wl.n_envs)))
 
