@@ -41,13 +41,12 @@ cudaError_t dev_alloc(T **p, size_t n) {
   return e;
 }
 
-const void *g_cfg_owner = nullptr;  // which engine's StepCfg sits in constant memory
-
 }  // namespace
 
 struct swb_engine {
   swb_config cfg;
   StepCfg step_cfg;
+  StepCfg *d_step_cfg = nullptr;  // device copy the step kernel reads (per engine)
   DevState st;
   int device = 0;
   int max_spans = 1;  // 1 while every uploaded shape is convex, else 4
@@ -104,14 +103,6 @@ __global__ void scatter_scenes_kernel(DevState st, int n, const int32_t *__restr
   st.p_pos_f32[d] = u8[1 * u8_stride + i];
   st.p_rgb[d] = rgb[i];
   for (int f = 0; f < 5; ++f) st.p_factors[d * 5 + f] = factors[(size_t)i * 5 + f];
-}
-
-int ensure_step_cfg(swb_engine *eng) {
-  if (g_cfg_owner != eng) {
-    CUDA_TRY(cudaMemcpyToSymbol(c_step, &eng->step_cfg, sizeof(StepCfg)));
-    g_cfg_owner = eng;
-  }
-  return 0;
 }
 
 template <typename T>
@@ -205,6 +196,7 @@ int swb_engine_create(const swb_config *cfg, swb_engine **out) {
   A(&st.p_factors, EKS * 5);
   double *d_verts = nullptr;
   int32_t *d_nv = nullptr;
+  A(&eng->d_step_cfg, 1);
   A(&d_verts, (size_t)SWB_NUM_SHAPES * SWB_MAX_VERTS * 2);
   A(&d_nv, SWB_NUM_SHAPES);
   if (!ok) {
@@ -216,6 +208,7 @@ int swb_engine_create(const swb_config *cfg, swb_engine **out) {
       swb_engine_destroy(eng);
       return fail("shape %d has %d vertices (max %d)", s, cfg->shape_n_verts[s], SWB_MAX_VERTS);
     }
+  CUDA_TRY(cudaMemcpy(eng->d_step_cfg, &eng->step_cfg, sizeof(StepCfg), cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(d_verts, cfg->shape_verts, sizeof cfg->shape_verts, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(d_nv, cfg->shape_n_verts, sizeof cfg->shape_n_verts, cudaMemcpyHostToDevice));
   st.shape_verts = d_verts;
@@ -237,7 +230,6 @@ void swb_engine_destroy(swb_engine *eng) {
   if (eng->copy_stream) cudaStreamDestroy(eng->copy_stream);
   for (auto &ev : eng->chunk_done) if (ev) cudaEventDestroy(ev);
   if (eng->copies_done) cudaEventDestroy(eng->copies_done);
-  if (g_cfg_owner == eng) g_cfg_owner = nullptr;
   delete eng;
 }
 
@@ -326,10 +318,9 @@ int swb_step(swb_engine *eng, const void *actions, int32_t action_dtype, const s
   if (!emb && action_dtype != SWB_DTYPE_F32 && action_dtype != SWB_DTYPE_F64)
     return fail("SelectMove/DragAndDrop actions must be float32 or float64 [E][4]");
   CUDA_TRY(cudaSetDevice(eng->device));
-  if (ensure_step_cfg(eng)) return 1;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int blocks = (eng->st.E + STEP_WARPS - 1) / STEP_WARPS;
-  step_kernel<<<blocks, STEP_WARPS * 32, 0, stream>>>(eng->st, actions, action_dtype, *out, 0);
+  step_kernel<<<blocks, STEP_WARPS * 32, 0, stream>>>(eng->st, eng->d_step_cfg, actions, action_dtype, *out, 0);
   eng->launches++;
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -341,10 +332,9 @@ static int launch_partial(swb_engine *eng, const void *actions, int32_t action_d
   if (!out->reward || !out->step_type || !out->success || !out->status)
     return fail("every swb_step_out pointer must be set");
   CUDA_TRY(cudaSetDevice(eng->device));
-  if (ensure_step_cfg(eng)) return 1;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int blocks = (eng->st.E + STEP_WARPS - 1) / STEP_WARPS;
-  step_kernel<<<blocks, STEP_WARPS * 32, 0, stream>>>(eng->st, actions, action_dtype, *out, mode);
+  step_kernel<<<blocks, STEP_WARPS * 32, 0, stream>>>(eng->st, eng->d_step_cfg, actions, action_dtype, *out, mode);
   eng->launches++;
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -452,6 +442,7 @@ static int launch_render(swb_engine *eng, swb_raster *r, uint8_t *frames, uint8_
   targets.dst[0] = frames;
   targets.n = 1;
   targets.env_offset = 0;
+  targets.self = 0;
   return launch_render_targets(eng, r, targets, status, stream, env_base, env_count);
 }
 
@@ -485,6 +476,7 @@ int swb_step_render_gather(swb_engine *eng, swb_raster *r, const void *actions,
   }
   targets.n = n_dst;
   targets.env_offset = (int)env_offset;
+  targets.self = (int)((env_offset / (eng ? eng->st.E : 1)) % n_dst);
   if (swb_step(eng, actions, action_dtype, out, stream_)) return 1;
   return launch_render_targets(eng, r, targets, out->status, static_cast<cudaStream_t>(stream_));
 }

@@ -33,8 +33,8 @@ struct DevState {
   const int32_t *shape_n;     // [13]
 };
 
-// action space + episode + task tree, kept in constant memory (one engine per process
-// is the common case; the table is re-uploaded when another engine launches).
+// action space + episode + task tree; every engine keeps its own copy in device memory and
+// hands the step kernel a pointer to it.
 struct StepCfg {
   int32_t action_kind;
   double action_scale;

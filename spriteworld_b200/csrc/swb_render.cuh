@@ -50,6 +50,7 @@ struct RenderTargets {
   uint8_t *dst[SWB_MAX_PEERS];
   int n;
   int env_offset;
+  int self;  // index of this rank's own buffer in dst
 };
 
 struct RenderLayout {
@@ -171,7 +172,7 @@ __device__ unsigned long long g_phase_clk[16];
 #endif
 
 template <bool kPeers>  // kPeers: also store the frame into the other ranks' buffers
-__global__ void __launch_bounds__(R_THREADS)
+__global__ void __launch_bounds__(R_THREADS, 5)
 render_kernel(DevState st, RasterDev rd, const RenderLayout L, const RenderTargets targets,
               int env_base) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -209,6 +210,7 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, const RenderTarge
   // phase-B view of the scratch area: per-row crossing lists
   const int CAP = L.cap;
   __shared__ int s_overflow;
+  __shared__ uint8_t *s_dst[SWB_MAX_PEERS];  // kPeers: the targets, indexable at run time
 
   const int yo_b0 = band * rd.band_rows;
   const int yo_b1 = min(yo_b0 + rd.band_rows, rd.H);
@@ -231,6 +233,7 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, const RenderTarge
   constexpr int NWARP = R_THREADS / 32;
   const int lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_overflow = 0;
+  if (kPeers && tid < SWB_MAX_PEERS) s_dst[tid] = targets.dst[tid];
   const int cur = st.cursor[e];
   // tables first: their loads overlap the sprite records' dependent loads below
 #pragma unroll 1
@@ -771,10 +774,18 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, const RenderTarge
     __syncthreads();
     if (tid == 0) {
       const uint32_t src = (uint32_t)__cvta_generic_to_shared(s_frame);
-#pragma unroll 1
-      for (int t = 0; t < (kPeers ? targets.n : 1); ++t)
+      // peers in an order rotated by rank and CTA, so that at any moment the ranks' copies are
+      // spread over all receivers instead of all hitting rank 0 first, then rank 1, ...
+      int t = 0;
+      if (kPeers) {  // (self + 1 + blockIdx.x) mod n without a division (n <= 8)
+        t = targets.self + 1 + (int)(blockIdx.x & 7u);
+        while (t >= targets.n) t -= targets.n;
+      }
+      for (int i = 0; i < (kPeers ? targets.n : 1); ++i) {
         asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                     : : "l"(targets.dst[t] + band_off), "r"(src), "r"(n_bytes) : "memory");
+                     : : "l"((kPeers ? s_dst[t] : targets.dst[0]) + band_off), "r"(src), "r"(n_bytes) : "memory");
+        if (kPeers && ++t == targets.n) t = 0;
+      }
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       // the CTA's shared memory must stay until the engine has read it
       asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");

@@ -12,8 +12,6 @@
 
 namespace swb {
 
-__constant__ StepCfg c_step;
-
 constexpr int STEP_WARPS = 4;
 
 struct WarpSprites {
@@ -275,7 +273,8 @@ __device__ TaskVal clustering(const swb_task_node &nd, const WarpSprites &ws, in
 }
 
 // whole task tree; root = last node (tasks.py:288-296 for MetaAggregated)
-__device__ void task_eval(const WarpSprites &ws, int S, double *reward, int *success, int *status) {
+__device__ void task_eval(const StepCfg &c_step, const WarpSprites &ws, int S, double *reward,
+                          int *success, int *status) {
   TaskVal val[SWB_MAX_NODES];
   const int nn = c_step.n_nodes;
   for (int i = 0; i < nn; i++) {
@@ -325,8 +324,11 @@ __device__ void task_eval(const WarpSprites &ws, int S, double *reward, int *suc
 }
 
 __global__ void __launch_bounds__(STEP_WARPS * 32)
-step_kernel(DevState st, const void *__restrict__ actions, int action_dtype, swb_step_out out,
-            int mode) {
+step_kernel(DevState st, const StepCfg *__restrict__ step_cfg, const void *__restrict__ actions,
+            int action_dtype, swb_step_out out, int mode) {
+  // the engine's own copy of the action space / episode / task tree, in global memory: a
+  // kernel of engine A queued behind a launch of engine B still reads A's table
+  const StepCfg &c_step = *step_cfg;
   // mode 0: Environment.step; 1: task.reward/success of the live state only;
   // 2: action_space.step only (no velocity update, task or counters)
   __shared__ WarpSprites s_ws[STEP_WARPS];
@@ -451,7 +453,7 @@ step_kernel(DevState st, const void *__restrict__ actions, int action_dtype, swb
   if (lane == 0) {
     double tr;
     int succ;
-    task_eval(ws, S, &tr, &succ, &status);
+    task_eval(c_step, ws, S, &tr, &succ, &status);
     if (mode == 1) {
       out.reward[e] = tr;
       out.step_type[e] = (int8_t)SWB_STEP_MID;

@@ -122,3 +122,33 @@ class Episodes(object):
                             self.meta['bg']) if with_raster else None)
     pool = records_from_arrays(self.scenes)
     return cfg, tab, rc, pool
+
+
+def workload_oracle(wl, scenes, n_envs, pool_depth, env_subset=None, max_episode_length=None):
+  """BatchOracle over (a subset of the envs of) the scene pool a workload engine was built
+  with: `scenes` is what workloads.build_engine returned, laid out (n_envs * pool_depth, S).
+  Envs are independent, so an oracle over a subset of envs reproduces exactly those envs."""
+  from spriteworld_b200 import constants
+  idx = np.arange(n_envs) if env_subset is None else np.asarray(env_subset)
+  rec = np.zeros((n_envs * pool_depth, wl.n_slots), oracle.SPRITE_DTYPE)
+  for f in ('x', 'y', 'm00', 'm01', 'm10', 'm11', 'vx', 'vy', 'member', 'shape', 'pos_f32', 'rgb'):
+    rec[f] = scenes[f]
+  pool = rec.reshape(n_envs, pool_depth, wl.n_slots)[idx]
+  cfg = env_cfg_from_meta(dict(
+      action=wl.action, keep_in_frame=True,
+      max_episode_length=max_episode_length or wl.max_episode_length,
+      nodes=[dict(n, goal=list(n.get('goal', (0, 0))), weights=list(n.get('weights', (1, 1))))
+             if n['kind'] == 'find_goal' else n for n in wl.nodes]))
+  tab = oracle.shape_table(constants.SHAPES)
+  rc = oracle.raster_cfg(wl.image_size[0], wl.image_size[1], wl.anti_aliasing)
+  return oracle.BatchOracle(cfg, tab, rc, pool)
+
+
+def step_oracle_threads(bo, actions, n_threads):
+  """One BatchOracle.step split over threads (the C call releases the GIL)."""
+  from concurrent.futures import ThreadPoolExecutor
+  n_threads = max(1, min(n_threads, bo.E))
+  edges = np.linspace(0, bo.E, n_threads + 1).astype(int)
+  with ThreadPoolExecutor(n_threads) as ex:
+    list(ex.map(lambda i: bo.step(actions, int(edges[i]), int(edges[i + 1])), range(n_threads)))
+  return bo
