@@ -43,22 +43,31 @@ cudaError_t dev_alloc(T **p, size_t n) {
 
 }  // namespace
 
+// One staging slot of swb_upload_scenes: a pinned host block and its device twin, laid out
+// [8 x f64][member u32][rgb u32][factors 5 x f32][dst i32][shape u8][pos_f32 u8] for `cap`
+// scenes, moved with ONE cudaMemcpyAsync and scattered into the pool by one kernel.
+struct UploadSlot {
+  size_t cap = 0;          // scenes
+  size_t bytes = 0;
+  unsigned char *host = nullptr, *dev = nullptr;
+  cudaEvent_t done = nullptr;  // recorded after the scatter kernel that reads `dev`
+  bool in_flight = false;
+};
+
 struct swb_engine {
   swb_config cfg;
   StepCfg step_cfg;
   StepCfg *d_step_cfg = nullptr;  // device copy the step kernel reads (per engine)
+  unsigned *d_work = nullptr;     // render kernel's work counter (monotonic, see render_kernel)
+  unsigned work_base = 0;         // its value when the next launch starts
+  int n_sms = 1;
   DevState st;
   int device = 0;
   int max_spans = 1;  // 1 while every uploaded shape is convex, else 4
   int64_t launches = 0;
-  // staging for scene uploads (device), grown on demand
-  size_t stage_cap = 0;
-  double *g_f64 = nullptr;    // [8][cap*S]
-  uint32_t *g_member = nullptr;
-  uint8_t *g_u8 = nullptr;    // [2][cap*S]
-  uint32_t *g_rgb = nullptr;
-  float *g_factors = nullptr;
-  int32_t *g_dst = nullptr;   // [cap] destination scene index e*K+k
+  // staging for scene uploads (pinned host + device), grown on demand, double-buffered
+  UploadSlot upload_slots[2];
+  int upload_next = 0;
   std::vector<void *> owned;
   // buffers of swb_step_host
   void *h_actions = nullptr;
@@ -83,7 +92,8 @@ namespace {
 __global__ void scatter_scenes_kernel(DevState st, int n, const int32_t *__restrict__ dst,
                                       const double *__restrict__ f64, size_t f64_stride,
                                       const uint32_t *__restrict__ member,
-                                      const uint8_t *__restrict__ u8, size_t u8_stride,
+                                      const uint8_t *__restrict__ shape,
+                                      const uint8_t *__restrict__ pos_f32,
                                       const uint32_t *__restrict__ rgb,
                                       const float *__restrict__ factors) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -99,8 +109,8 @@ __global__ void scatter_scenes_kernel(DevState st, int n, const int32_t *__restr
   st.p_vx[d] = f64[6 * f64_stride + i];
   st.p_vy[d] = f64[7 * f64_stride + i];
   st.p_member[d] = member[i];
-  st.p_shape[d] = u8[0 * u8_stride + i];
-  st.p_pos_f32[d] = u8[1 * u8_stride + i];
+  st.p_shape[d] = shape[i];
+  st.p_pos_f32[d] = pos_f32[i];
   st.p_rgb[d] = rgb[i];
   for (int f = 0; f < 5; ++f) st.p_factors[d * 5 + f] = factors[(size_t)i * 5 + f];
 }
@@ -120,7 +130,6 @@ int upload_axis(swb_raster *r, const AxisHost &h, AxisTables *d) {
   if (upload_vec(r, h.win_len, &d->win_len)) return 1;
   if (upload_vec(r, h.win_cls, &d->win_cls)) return 1;
   if (upload_vec(r, h.prefix, &d->prefix)) return 1;
-  if (upload_vec(r, h.program, &d->program)) return 1;
   if (upload_vec(r, h.first_out, &d->first_out)) return 1;
   if (upload_vec(r, h.last_out, &d->last_out)) return 1;
   return 0;
@@ -165,6 +174,9 @@ int swb_engine_create(const swb_config *cfg, swb_engine **out) {
   swb_engine *eng = new swb_engine();
   eng->cfg = *cfg;
   eng->device = cfg->device;
+  if (cudaDeviceGetAttribute(&eng->n_sms, cudaDevAttrMultiProcessorCount, cfg->device) != cudaSuccess ||
+      eng->n_sms < 1)
+    eng->n_sms = 148;
   StepCfg &sc = eng->step_cfg;
   memset(&sc, 0, sizeof sc);
   sc.action_kind = cfg->action_kind;
@@ -197,6 +209,8 @@ int swb_engine_create(const swb_config *cfg, swb_engine **out) {
   double *d_verts = nullptr;
   int32_t *d_nv = nullptr;
   A(&eng->d_step_cfg, 1);
+  A(&eng->d_work, 1);
+  A(&st.scene_serial, st.E);
   A(&d_verts, (size_t)SWB_NUM_SHAPES * SWB_MAX_VERTS * 2);
   A(&d_nv, SWB_NUM_SHAPES);
   if (!ok) {
@@ -223,14 +237,32 @@ void swb_engine_destroy(swb_engine *eng) {
   if (!eng) return;
   cudaSetDevice(eng->device);
   for (void *p : eng->owned) cudaFree(p);
-  cudaFree(eng->g_f64); cudaFree(eng->g_member); cudaFree(eng->g_u8); cudaFree(eng->g_rgb);
-  cudaFree(eng->g_factors); cudaFree(eng->g_dst);
+  for (auto &slot : eng->upload_slots) {
+    if (slot.in_flight) cudaEventSynchronize(slot.done);
+    if (slot.host) cudaFreeHost(slot.host);
+    if (slot.dev) cudaFree(slot.dev);
+    if (slot.done) cudaEventDestroy(slot.done);
+  }
   cudaFree(eng->h_actions); cudaFree(eng->h_out.reward); cudaFree(eng->h_out.step_type);
   cudaFree(eng->h_out.success); cudaFree(eng->h_out.status); cudaFree(eng->h_frames);
   if (eng->copy_stream) cudaStreamDestroy(eng->copy_stream);
   for (auto &ev : eng->chunk_done) if (ev) cudaEventDestroy(ev);
   if (eng->copies_done) cudaEventDestroy(eng->copies_done);
   delete eng;
+}
+
+static size_t upload_layout(size_t cap, int S, size_t off[7]) {
+  const size_t capS = cap * S;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) & ~(size_t)255; return r; };
+  off[0] = take(capS * 8 * sizeof(double));   // f64 x 8
+  off[1] = take(capS * sizeof(uint32_t));     // member
+  off[2] = take(capS * sizeof(uint32_t));     // rgb
+  off[3] = take(capS * 5 * sizeof(float));    // factors
+  off[4] = take(cap * sizeof(int32_t));       // dst
+  off[5] = take(capS);                        // shape
+  off[6] = take(capS);                        // pos_f32
+  return o;
 }
 
 int swb_upload_scenes(swb_engine *eng, const swb_scene_soa *sc, const int32_t *env_ids,
@@ -241,11 +273,13 @@ int swb_upload_scenes(swb_engine *eng, const swb_scene_soa *sc, const int32_t *e
   CUDA_TRY(cudaSetDevice(eng->device));
   const int S = eng->st.S;
   const size_t nS = (size_t)n * S;
-  std::vector<int32_t> dst(n);
+  const double *f64_src[8] = {sc->x, sc->y, sc->m00, sc->m01, sc->m10, sc->m11, sc->vx, sc->vy};
+  for (int a = 0; a < 8; ++a)
+    if (!f64_src[a]) return fail("swb_upload_scenes: null f64 array %d", a);
+  if (!sc->member || !sc->shape || !sc->pos_f32 || !sc->rgb) return fail("swb_upload_scenes: null array");
   for (int i = 0; i < n; ++i) {
     if (env_ids[i] < 0 || env_ids[i] >= eng->st.E) return fail("env id %d out of range", env_ids[i]);
     if (ring_slots[i] < 0 || ring_slots[i] >= eng->st.K) return fail("ring slot %d out of range", ring_slots[i]);
-    dst[i] = env_ids[i] * eng->st.K + ring_slots[i];
   }
   for (size_t i = 0; i < nS; ++i) {
     const int sh = sc->shape[i];
@@ -253,48 +287,56 @@ int swb_upload_scenes(swb_engine *eng, const swb_scene_soa *sc, const int32_t *e
     if (sh > 6) eng->max_spans = 4;  // stars / spokes: several spans per canvas row
     if (sh && eng->cfg.shape_n_verts[sh] < 3) return fail("shape %d has no vertex table", sh);
   }
-  if ((size_t)n > eng->stage_cap) {
-    CUDA_TRY(cudaStreamSynchronize(stream));
-    cudaFree(eng->g_f64); cudaFree(eng->g_member); cudaFree(eng->g_u8); cudaFree(eng->g_rgb);
-    cudaFree(eng->g_factors); cudaFree(eng->g_dst);
-    eng->stage_cap = 0;
-    const size_t cap = (size_t)n, capS = cap * S;
-    CUDA_TRY(cudaMalloc(&eng->g_f64, capS * 8 * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&eng->g_member, capS * sizeof(uint32_t)));
-    CUDA_TRY(cudaMalloc(&eng->g_u8, capS * 2));
-    CUDA_TRY(cudaMalloc(&eng->g_rgb, capS * sizeof(uint32_t)));
-    CUDA_TRY(cudaMalloc(&eng->g_factors, capS * 5 * sizeof(float)));
-    CUDA_TRY(cudaMalloc(&eng->g_dst, cap * sizeof(int32_t)));
-    eng->stage_cap = cap;
+  // two staging slots alternate, so the host packs upload i+1 while upload i is in flight; a
+  // slot is reused only after the scatter kernel that read it has finished (its event)
+  UploadSlot &slot = eng->upload_slots[eng->upload_next];
+  eng->upload_next ^= 1;
+  if (slot.in_flight) {
+    CUDA_TRY(cudaEventSynchronize(slot.done));
+    slot.in_flight = false;
   }
-  const size_t stride = eng->stage_cap * S;
-  const double *f64_src[8] = {sc->x, sc->y, sc->m00, sc->m01, sc->m10, sc->m11, sc->vx, sc->vy};
-  for (int a = 0; a < 8; ++a) {
-    if (!f64_src[a]) return fail("swb_upload_scenes: null f64 array %d", a);
-    CUDA_TRY(cudaMemcpyAsync(eng->g_f64 + a * stride, f64_src[a], nS * sizeof(double),
-                             cudaMemcpyHostToDevice, stream));
+  if ((size_t)n > slot.cap) {
+    if (slot.host) cudaFreeHost(slot.host);
+    if (slot.dev) cudaFree(slot.dev);
+    slot.host = slot.dev = nullptr;
+    slot.cap = 0;
+    size_t off[7];
+    const size_t cap = std::max<size_t>((size_t)n, 256);
+    const size_t bytes = upload_layout(cap, S, off);
+    CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&slot.host), bytes));
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&slot.dev), bytes));
+    if (!slot.done) CUDA_TRY(cudaEventCreateWithFlags(&slot.done, cudaEventDisableTiming));
+    slot.cap = cap;
+    slot.bytes = bytes;
   }
-  if (!sc->member || !sc->shape || !sc->pos_f32 || !sc->rgb) return fail("swb_upload_scenes: null array");
-  CUDA_TRY(cudaMemcpyAsync(eng->g_member, sc->member, nS * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
-  CUDA_TRY(cudaMemcpyAsync(eng->g_u8, sc->shape, nS, cudaMemcpyHostToDevice, stream));
-  CUDA_TRY(cudaMemcpyAsync(eng->g_u8 + stride, sc->pos_f32, nS, cudaMemcpyHostToDevice, stream));
-  std::vector<uint32_t> rgb(nS);
+  size_t off[7];
+  upload_layout(slot.cap, S, off);
+  const size_t stride = slot.cap * S;
+  unsigned char *h = slot.host;
+  for (int a = 0; a < 8; ++a)
+    memcpy(h + off[0] + a * stride * sizeof(double), f64_src[a], nS * sizeof(double));
+  memcpy(h + off[1], sc->member, nS * sizeof(uint32_t));
+  uint32_t *rgb = reinterpret_cast<uint32_t *>(h + off[2]);
   for (size_t i = 0; i < nS; ++i)
     rgb[i] = (uint32_t)sc->rgb[3 * i] | ((uint32_t)sc->rgb[3 * i + 1] << 8) | ((uint32_t)sc->rgb[3 * i + 2] << 16);
-  CUDA_TRY(cudaMemcpyAsync(eng->g_rgb, rgb.data(), nS * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
-  if (sc->factors) {
-    CUDA_TRY(cudaMemcpyAsync(eng->g_factors, sc->factors, nS * 5 * sizeof(float), cudaMemcpyHostToDevice, stream));
-  } else {
-    CUDA_TRY(cudaMemsetAsync(eng->g_factors, 0, nS * 5 * sizeof(float), stream));
-  }
-  CUDA_TRY(cudaMemcpyAsync(eng->g_dst, dst.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+  if (sc->factors) memcpy(h + off[3], sc->factors, nS * 5 * sizeof(float));
+  else memset(h + off[3], 0, nS * 5 * sizeof(float));
+  int32_t *dst = reinterpret_cast<int32_t *>(h + off[4]);
+  for (int i = 0; i < n; ++i) dst[i] = env_ids[i] * eng->st.K + ring_slots[i];
+  memcpy(h + off[5], sc->shape, nS);
+  memcpy(h + off[6], sc->pos_f32, nS);
+  // everything up to the end of the last used array, in one copy
+  CUDA_TRY(cudaMemcpyAsync(slot.dev, slot.host, off[6] + nS, cudaMemcpyHostToDevice, stream));
   const int threads = 256, blocks = (int)((nS + threads - 1) / threads);
-  scatter_scenes_kernel<<<blocks, threads, 0, stream>>>(eng->st, n, eng->g_dst, eng->g_f64, stride,
-                                                        eng->g_member, eng->g_u8, stride, eng->g_rgb,
-                                                        eng->g_factors);
+  unsigned char *d = slot.dev;
+  scatter_scenes_kernel<<<blocks, threads, 0, stream>>>(
+      eng->st, n, reinterpret_cast<const int32_t *>(d + off[4]), reinterpret_cast<const double *>(d + off[0]),
+      stride, reinterpret_cast<const uint32_t *>(d + off[1]), d + off[5], d + off[6],
+      reinterpret_cast<const uint32_t *>(d + off[2]), reinterpret_cast<const float *>(d + off[3]));
   eng->launches++;
   CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaStreamSynchronize(stream));  // host staging vectors die here
+  CUDA_TRY(cudaEventRecord(slot.done, stream));
+  slot.in_flight = true;
   return 0;
 }
 
@@ -377,26 +419,36 @@ int swb_raster_create(swb_engine *eng, int32_t width, int32_t height, int32_t aa
   rd.max_spans = 1;
   rd.ncls_x = r->ax.n_cls;
   rd.ncls_y = r->ay.n_cls;
-  rd.ny_cap = std::max(1, (HT_ROWS - 32) / rd.aa + 1);
-  rd.a5_cls = -1;
-  for (int c = 0; c < r->ay.n_cls; ++c) {
-    const int32_t *prog = r->ay.program.data() + (size_t)c * PROG_STRIDE;
-    if (prog[1] >> 16) {
-      rd.a5_cls = c;
-      for (int k = 0; k < 12; ++k) rd.a5_coef[k] = prog[2 + 2 * k + 1];
-      rd.a5_coef[12] = prog[2 + 2 * 16 + 1];
-    }
-  }
   int rows = 0;
   for (int b = 0; b < rd.n_bands; ++b) {
     const int y0 = b * rd.band_rows, y1 = std::min(y0 + rd.band_rows, height) - 1;
-    rows = std::max(rows, r->ay.win_min[y1] + r->ay.win_len[y1] - r->ay.win_min[y0]);
+    // the kernel counts a band's canvas rows from a multiple of four
+    rows = std::max(rows, r->ay.win_min[y1] + r->ay.win_len[y1] - (r->ay.win_min[y0] & ~3));
+    // a tile of TILE_BLOCKS blocks of eight output rows must fit the H tile's row length
+    for (int t0 = y0; t0 <= y1; t0 += 8) {
+      const int t1 = std::min(t0 + 8 * TILE_BLOCKS - 1, y1);
+      const int span = r->ay.win_min[t1] + r->ay.win_len[t1] - (r->ay.win_min[t0] & ~3);
+      if (span > 4 * HT_ROWW) {
+        delete r;
+        return fail("vertical tap windows of %d output rows span %d canvas rows (limit %d)",
+                    8 * TILE_BLOCKS, span, 4 * HT_ROWW);
+      }
+    }
   }
   r->smem_rows = rows;
-  if (upload_axis(r, r->ax, &rd.ax) || upload_axis(r, r->ay, &rd.ay)) {
+  VFragHost vf;
+  if (!build_vfrag(r->ay, &vf, &err)) {
+    delete r;
+    return fail("%s", err.c_str());
+  }
+  rd.v_nks = vf.nks;
+  const uint32_t *d_frag = nullptr;
+  if (upload_axis(r, r->ax, &rd.ax) || upload_axis(r, r->ay, &rd.ay) ||
+      upload_vec(r, vf.blk_cls, &rd.v_blk_cls) || upload_vec(r, vf.frag, &d_frag)) {
     swb_raster_destroy(r);
     return 1;
   }
+  rd.v_frag = reinterpret_cast<const uint2 *>(d_frag);  // cudaMalloc: 256-byte aligned
   *out = r;
   return 0;
 }
@@ -429,8 +481,13 @@ static int launch_render_targets(swb_engine *eng, swb_raster *r, const RenderTar
   st.render_status = status;
   if (env_count < 0) env_count = eng->st.E - env_base;
   if (env_count <= 0) return 0;
-  dim3 grid(env_count, rd.n_bands);
-  kernel<<<grid, R_THREADS, L.total, stream>>>(st, rd, L, targets, env_base);
+  // persistent CTAs: one per resident slot (or per item if there are fewer), claiming
+  // (env, band) items from the engine's counter; see render_kernel
+  const int n_items = env_count * rd.n_bands;
+  const int grid = std::min(n_items, eng->n_sms * R_CTAS_PER_SM);
+  kernel<<<grid, R_THREADS, L.total, stream>>>(st, rd, L, targets, env_base, n_items, eng->d_work,
+                                               eng->work_base);
+  eng->work_base += (unsigned)(n_items + grid);  // every CTA's last claim fails
   eng->launches++;
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -594,6 +651,12 @@ int swb_state_pointers(swb_engine *eng, double **pos_x, double **pos_y, int32_t 
   if (cursor) *cursor = eng->st.cursor;
   if (step_count) *step_count = eng->st.step_count;
   if (reset_next) *reset_next = eng->st.reset_next;
+  return 0;
+}
+
+int swb_scene_serial_pointer(swb_engine *eng, int32_t **scene_serial) {
+  if (!eng || !scene_serial) return fail("swb_scene_serial_pointer: null argument");
+  *scene_serial = eng->st.scene_serial;
   return 0;
 }
 

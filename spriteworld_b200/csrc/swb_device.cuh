@@ -4,6 +4,7 @@
 //   live state   pos_x, pos_y            [E*S] f64   (float32-valued where pos_f32)
 //                cursor, step_count      [E]   i32
 //                reset_next              [E]   u8
+//                scene_serial            [E]   i32  (how many scenes the env has started)
 //   scene pool   x0,y0,m00..m11,vx,vy    [E*K*S] f64
 //                member                  [E*K*S] u32
 //                shape,pos_f32           [E*K*S] u8
@@ -23,6 +24,7 @@ struct DevState {
   double *pos_x, *pos_y;
   int32_t *cursor, *step_count;
   uint8_t *reset_next;
+  int32_t *scene_serial;   // [E] scenes the env has started so far (monotonic; ring slot = cursor)
   uint8_t *render_status;  // [E] SWB_ENV_SPAN_OVERFLOW from the last render
   double *p_x, *p_y, *p_m00, *p_m01, *p_m10, *p_m11, *p_vx, *p_vy;
   uint32_t *p_member;
@@ -51,7 +53,6 @@ struct AxisTables {
   const uint8_t *win_len;    // [n_out]  taps (<= 32)
   const uint8_t *win_cls;    // [n_out]  class = distinct tap vector
   const int32_t *prefix;     // [n_cls][33] prefix sums of the tap vector, prefix[len] = total
-  const int32_t *program;    // [n_cls][PROG_STRIDE] paired-tap program (see swb_tables.h)
   const int16_t *first_out;  // [n_in] first output whose window contains input index i
   const int16_t *last_out;   // [n_in] last  output whose window contains input index i
 };
@@ -63,14 +64,13 @@ struct RasterDev {
   int n_bands;
   int max_spans;  // spans kept per (sprite, canvas row)
   int ncls_x, ncls_y;  // distinct tap vectors per axis
-  int ny_cap;  // output rows per render tile: (ny_cap-1)*aa + 32 canvas rows fit the H buffer
-  // vertical-pass fast path: class id and the 13 distinct coefficients of the interior tap
-  // vector of a 5x reduction (taps k and 28-k equal; 4,9,19,24,29 zero; 14 the centre)
-  int a5_cls;
-  int32_t a5_coef[13];
+  // vertical pass on the integer tensor pipe (mma.sync m16n8k32 u8 x s8 -> s32): per block of
+  // eight output rows the 22-bit tap matrix, cut into three signed 8-bit limbs and laid out as
+  // the instruction's B fragments (see swb_tables.h build_vfrag)
+  int v_nks;                 // k-steps (32 canvas rows each) a block's taps span
+  const uint8_t *v_blk_cls;  // [ceil(H/8)] class (distinct coefficient matrix) of each block
+  const uint2 *v_frag;       // [n_cls][v_nks][3 limbs][32 lanes] {b0, b1}
   AxisTables ax, ay;
 };
-
-constexpr int PROG_STRIDE = 2 + 2 * 16 + 2 * 32;  // header, <=16 pairs, <=32 singles
 
 }  // namespace swb

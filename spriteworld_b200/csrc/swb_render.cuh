@@ -14,16 +14,25 @@
 //                 ROUND_UP/ROUND_DOWN rule, add horizontal edges, and fold the spans into
 //                 the row's list of VISIBLE segments (x range + sprite), i.e. the painter's
 //                 algorithm resolved once per canvas row.
-//   C  per sprite region (the outputs whose 2-D tap window can see the sprite), in tiles
-//      sized to a 20 KB buffer of H values:
-//        H  horizontal LANCZOS pass of the canvas rows the tile needs.  A canvas row is piecewise constant, so an output is
-//           bg*K + sum_segments (colour-bg) * (P[b]-P[a]) with P the prefix sums of the
-//           22-bit tap vector and [a, b) the segment clamped to the tap window
-//           (branch-free).  clip8'ed like Pillow's uint8 intermediate.
-//        V  vertical pass over the tile's H values (paired taps: equal coefficients share
-//           one multiply), clip8, written into the frame staged in shared memory.
-//   D  the staged frame (background + tiles) goes to HBM as 128-bit stores, rows flipped
-//      (np.flipud, pil_renderer.py:90).
+//   C  per sprite region (the outputs whose 2-D tap window can see the sprite), in tiles of
+//      up to three blocks of eight output rows x 21 columns:
+//        H  horizontal LANCZOS pass of the canvas rows the tile needs.  A canvas row is
+//           piecewise constant, so an output is bg*K + sum_segments (colour-bg) * (P[b]-P[a])
+//           with P the prefix sums of the 22-bit tap vector and [a, b) the segment clamped
+//           to the tap window (branch-free), clip8'ed like Pillow's uint8 intermediate.
+//           A thread owns two columns of four consecutive canvas rows and stores the four
+//           uint8 results of a (column, channel) as one word: the H tile is laid out
+//           [column*3 + channel][canvas row / 4], i.e. as the k-contiguous A operand of
+//        V  the vertical pass on the integer tensor pipe: per block of eight output rows a
+//           banded contraction out[yo][n] = sum_r K[yo][r] * H[r][n], mma.sync.m16n8k32
+//           u8 x s8 -> s32 with the 22-bit taps cut into three signed 8-bit limbs (exact:
+//           the sums stay below 2^31), clip8, written into the frame staged in shared memory.
+//   D  the staged frame (background + tiles), rows flipped (np.flipud, pil_renderer.py:90),
+//      goes to HBM through the bulk-copy engine.
+//
+// The kernel is persistent: a CTA claims (env, band) items from a counter until none is
+// left, so the axis tables are loaded once per CTA, a frame's write-out overlaps the next
+// frame's set-up, and no SM idles in a last partial wave.
 //
 // All pixel arithmetic is integer and associative, so the result is bit-identical to
 // Pillow's; the float32 edge arithmetic uses explicit _rn intrinsics (no FMA).
@@ -35,10 +44,17 @@
 namespace swb {
 
 constexpr int R_THREADS = 256;
+#ifndef SWB_RENDER_CTAS
+#define SWB_RENDER_CTAS 5
+#endif
+constexpr int R_CTAS_PER_SM = SWB_RENDER_CTAS;  // resident CTAs per SM the register budget is set for
 constexpr int H_NC = 2;           // output columns one H-pass thread owns
-constexpr int TILE_X_MAX = 20;    // output columns per tile = row stride of the H buffer
-constexpr int HT_ROWS = 112;      // canvas rows a tile's H buffer holds
-constexpr int HT_ITEMS = HT_ROWS * TILE_X_MAX;
+constexpr int TILE_X_MAX = 21;    // output columns per tile: 63 (column, channel) rows of the H tile
+constexpr int TILE_BLOCKS = 3;    // blocks of eight output rows per tile
+constexpr int HT_N = 64;          // (column, channel) rows of the H tile = 4 MMA row tiles of 16
+constexpr int HT_ROWW = 44;       // words per row = 176 canvas rows; = 4 mod 8: fragment loads hit 32 banks
+constexpr int HT_PAD = 24;        // words the last row's k-steps may read past its end (zero taps)
+constexpr int HT_WORDS = HT_N * HT_ROWW + HT_PAD;
 constexpr int MAX_ROW_SPANS = 12;
 constexpr int EV = SWB_MAX_VERTS;  // edge slots per sprite
 static_assert(EV == 32, "phase A maps one lane to one vertex / edge");
@@ -56,13 +72,14 @@ struct RenderTargets {
 struct RenderLayout {
   int S, rows, M, band_rows, W, aa, ncx, ncy, cap;
   int off_meta, off_edge_i, off_edge_f, off_edge_yr, off_hl, off_region;
-  int off_nseg, off_segs, off_prefix, off_xwin, off_ywin, off_scratch, off_frame, total;
+  int off_nseg, off_rel, off_segs, off_prefix, off_xwin, off_ywin, off_scratch, off_frame, total;
   int scratch_bytes, segcap;
   __host__ __device__ RenderLayout(int S_, int rows_, int M_, int band_rows_, int W_, int aa_,
                                    int ncx_, int ncy_)
       : S(S_), rows(rows_), M(M_), band_rows(band_rows_), W(W_), aa(aa_), ncx(ncx_), ncy(ncy_) {
     int o = 0;
     auto take = [&](int bytes) { int r = o; o += (bytes + 15) & ~15; return r; };
+    take(SWB_MAX_SLOTS * 16);              // offset 0: colour - background per channel (int4 per sprite)
     off_meta = take(S * (12 + 8) * 4);     // 12 plan ints + 8 active-edge masks per sprite
     off_edge_i = take(S * EV * 2 * 4);     // x0, y0
     off_edge_f = take(S * EV * 3 * 4);     // dx, ovs (override on the first row), ove (on the last row)
@@ -71,7 +88,8 @@ struct RenderLayout {
     off_region = take(S * 4 * 2);
     // visible segments kept per canvas row: n one-span sprites leave at most 2n-1 pieces
     segcap = M > 1 ? 16 : (2 * S < 4 ? 4 : (2 * S > 16 ? 16 : 2 * S));
-    off_nseg = take(rows);
+    off_nseg = take(((rows + 3) & ~3) + 8);  // +: quads of the H pass may end past the last row
+    off_rel = take(4 * HT_ROWW * 2);       // per canvas row of the current tile: first relevant segment | count << 8
     off_segs = take(rows * segcap * 4);
     off_prefix = take(ncx * 33 * 4);
     off_xwin = take(W * 4);                // per output column: win_min | len<<16 | cls<<24
@@ -81,7 +99,7 @@ struct RenderLayout {
     // spans of a chunk of sprites, so it must hold at least one sprite spanning every row
     const int frame_bytes = band_rows * W * 3;
     const int need_b = (cap + M) * 4 * rows;
-    int ht_bytes = HT_ITEMS * 4;           // one H value = r | g<<10 | b<<20
+    int ht_bytes = HT_WORDS * 4;           // one word = four canvas rows of one (column, channel)
     if (ht_bytes + ((frame_bytes + 15) & ~15) < need_b) ht_bytes = need_b - frame_bytes;
     off_scratch = take(ht_bytes);
     off_frame = take(frame_bytes);
@@ -171,13 +189,56 @@ __device__ unsigned long long g_phase_clk[16];
 #define SWB_MARK(id) do { } while (0)
 #endif
 
+__device__ __forceinline__ int4 lds_v4(uint32_t addr) {
+  int4 v;
+  asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u8 [%0], %1;" : : "r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+  return r;
+}
+// Pillow clip8 of a 22-bit fixed-point sum; the result register holds 0..255 (no re-masking)
+__device__ __forceinline__ uint32_t sat_u8_q22(int v) {
+  return (uint32_t)__vimin_s32_relu(v >> 22, 255);  // max(min(v >> 22, 255), 0), one instruction
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+// D(16x8, s32) += A(16x32, u8, row) * B(32x8, s8, col): the integer tensor pipe (SASS IMMA)
+__device__ __forceinline__ void mma_u8s8(int (&d)[4], const uint32_t (&a)[4], const uint2 b) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};"
+      : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y));
+}
+
+// The kernel's dynamic shared memory, at namespace scope so that its shared-window address
+// can be taken by name (mov.u32 r, symbol: a link-time constant; converting a generic pointer
+// costs five instructions on sm_100 and is rematerialised at every use)
+extern __shared__ __align__(16) unsigned char g_render_smem[];
+__device__ __forceinline__ uint32_t render_smem_base() {
+  uint32_t a;
+  asm("mov.u32 %0, _ZN3swb13g_render_smemE;" : "=r"(a));
+  return a;
+}
+__constant__ uint32_t c_prmt_insert[4] = {0x3214u, 0x3240u, 0x3410u, 0x4210u};  // byte i <- byte 0 of b
+
+// Persistent: CTAs claim (env, band) items with atomicAdd(work_counter) - work_base until
+// none is left (the host advances work_base by n_items + gridDim.x per launch, so the
+// counter never needs a reset).
 template <bool kPeers>  // kPeers: also store the frame into the other ranks' buffers
-__global__ void __launch_bounds__(R_THREADS, 5)
+__global__ void __launch_bounds__(R_THREADS, R_CTAS_PER_SM)
 render_kernel(DevState st, RasterDev rd, const RenderLayout L, const RenderTargets targets,
-              int env_base) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  const int e = env_base + blockIdx.x;  // frames is indexed by the absolute env id
-  const int band = blockIdx.y;
+              int env_base, int n_items, unsigned *work_counter, unsigned work_base) {
+  unsigned char *const smem = g_render_smem;
   const int tid = threadIdx.x;
   const int S = st.S;
 
@@ -190,6 +251,7 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, const RenderTarge
   int *s_pny = s_dr + S, *s_pnx = s_pny + S;
   int *s_pinvh = s_pnx + S, *s_hasov = s_pinvh + S;
   unsigned *s_emask = reinterpret_cast<unsigned *>(s_hasov + S);  // [S][8] active edges per row bucket
+  int4 *s_dcol = reinterpret_cast<int4 *>(smem);  // [SWB_MAX_SLOTS] at offset 0: its address is a constant
   // edge table: start vertex, slope, corner-join overrides on the first / last row
   int *e_x0 = reinterpret_cast<int *>(smem + L.off_edge_i);
   int *e_y0 = e_x0 + S * EV;
@@ -199,7 +261,7 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, const RenderTarge
   short *s_hl = reinterpret_cast<short *>(smem + L.off_hl);  // [S][EV][3]
   short *s_region = reinterpret_cast<short *>(smem + L.off_region);  // [S][4] yo0,yo1,xo0,xo1
   uint8_t *s_nseg = smem + L.off_nseg;
-  uint32_t *s_segs = reinterpret_cast<uint32_t *>(smem + L.off_segs);  // xs | xe<<12 | sprite<<24
+  uint32_t *s_segs = reinterpret_cast<uint32_t *>(smem + L.off_segs);  // xs | (xe+1)<<12 | sprite<<25
   const int SEGCAP = L.segcap;
   const int M = rd.max_spans;
   int32_t *s_prefix = reinterpret_cast<int32_t *>(smem + L.off_prefix);
@@ -210,44 +272,64 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, const RenderTarge
   // phase-B view of the scratch area: per-row crossing lists
   const int CAP = L.cap;
   __shared__ int s_overflow;
+  __shared__ int s_item;
   __shared__ uint8_t *s_dst[SWB_MAX_PEERS];  // kPeers: the targets, indexable at run time
 
-  const int yo_b0 = band * rd.band_rows;
-  const int yo_b1 = min(yo_b0 + rd.band_rows, rd.H);
-  const int n_yo = yo_b1 - yo_b0;
-  // canvas rows this band's vertical windows can touch
-  const int row_b0 = rd.ay.win_min[yo_b0];
-  const int row_b1 = rd.ay.win_min[yo_b1 - 1] + rd.ay.win_len[yo_b1 - 1];  // exclusive
-  const int n_rows = row_b1 - row_b0;
+  constexpr unsigned FULL = 0xFFFFFFFFu;
+  constexpr int NWARP = R_THREADS / 32;
+  const int lane = tid & 31, warp = tid >> 5;
+
+  // ---- once per CTA: the axis tables ------------------------------------------------------
+  if (kPeers && tid < SWB_MAX_PEERS) s_dst[tid] = targets.dst[tid];
+#pragma unroll 1
+  for (int i = tid; i < rd.ncls_x * 33; i += R_THREADS) s_prefix[i] = rd.ax.prefix[i];
+#pragma unroll 1
+  for (int i = tid; i < rd.W; i += R_THREADS)
+    s_xwin[i] = (uint32_t)(uint16_t)rd.ax.win_min[i] | ((uint32_t)rd.ax.win_len[i] << 16) |
+                ((uint32_t)rd.ax.win_cls[i] << 24);
+#pragma unroll 1
+  for (int i = tid; i < (((L.rows + 3) & ~3) + 8) / 4; i += R_THREADS) reinterpret_cast<uint32_t *>(s_nseg)[i] = 0u;
+  int band_loaded = -1;
+  bool copy_pending = false;  // thread 0: the previous frame's bulk copy may still read s_frame
 
 #ifdef SWB_PHASE_CLOCKS
   long long mark_ = clock64();
 #endif
+  for (;;) {
+  if (tid == 0) s_item = (int)(atomicAdd(work_counter, 1u) - work_base);
+  __syncthreads();
+  const int item = s_item;
+  if (item >= n_items) break;
+  const int band = rd.n_bands > 1 ? item % rd.n_bands : 0;
+  const int e = env_base + (rd.n_bands > 1 ? item / rd.n_bands : item);  // frames is indexed by the absolute env id
+
+  const int yo_b0 = band * rd.band_rows;
+  const int yo_b1 = min(yo_b0 + rd.band_rows, rd.H);
+  const int n_yo = yo_b1 - yo_b0;
+  // canvas rows this band's vertical windows can touch, from a row that is a multiple of four
+  // (the H tile packs four consecutive canvas rows into a word)
+  const int row_b0 = rd.ay.win_min[yo_b0] & ~3;
+  const int row_b1 = rd.ay.win_min[yo_b1 - 1] + rd.ay.win_len[yo_b1 - 1];  // exclusive
+  const int n_rows = row_b1 - row_b0;
+
   // ---- phase A: a warp per sprite, a lane per vertex / edge ------------------------------
   // Everything Pillow derives from the vertex list before it scans rows: integer vertices,
   // the edge table (add_edge), horizontal edges, extents, the corner joins -- plus this
   // kernel's own per-sprite plan (rows, output region, tiles, active-edge masks).  Neighbour
   // vertices come by shuffle, extents by warp reductions, "edges that share a start row" by
   // match_any; nothing leaves the warp until the barrier that ends the phase.
-  constexpr unsigned FULL = 0xFFFFFFFFu;
-  constexpr int NWARP = R_THREADS / 32;
-  const int lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_overflow = 0;
-  if (kPeers && tid < SWB_MAX_PEERS) s_dst[tid] = targets.dst[tid];
   const int cur = st.cursor[e];
-  // tables first: their loads overlap the sprite records' dependent loads below
-#pragma unroll 1
-  for (int i = tid; i < rd.ncls_x * 33; i += R_THREADS) s_prefix[i] = rd.ax.prefix[i];
+  // per-frame tables first: their loads overlap the sprite records' dependent loads below
 #pragma unroll 1
   for (int i = tid; i < (n_rows + 3) / 4; i += R_THREADS) reinterpret_cast<uint32_t *>(s_nseg)[i] = 0u;
+  if (band != band_loaded) {
 #pragma unroll 1
-  for (int i = tid; i < rd.W; i += R_THREADS)
-    s_xwin[i] = (uint32_t)(uint16_t)rd.ax.win_min[i] | ((uint32_t)rd.ax.win_len[i] << 16) |
-                ((uint32_t)rd.ax.win_cls[i] << 24);
-#pragma unroll 1
-  for (int i = tid; i < n_yo; i += R_THREADS)
-    s_ywin[i] = (uint32_t)(uint16_t)rd.ay.win_min[yo_b0 + i] | ((uint32_t)rd.ay.win_len[yo_b0 + i] << 16) |
-                ((uint32_t)rd.ay.win_cls[yo_b0 + i] << 24);
+    for (int i = tid; i < n_yo; i += R_THREADS)
+      s_ywin[i] = (uint32_t)(uint16_t)rd.ay.win_min[yo_b0 + i] | ((uint32_t)rd.ay.win_len[yo_b0 + i] << 16) |
+                  ((uint32_t)rd.ay.win_cls[yo_b0 + i] << 24);
+    band_loaded = band;
+  }
   for (int s = warp; s < S; s += NWARP) {
     // sprite record of this env's current scene (warp-uniform loads)
     const int scene = (e * st.K + cur) * S + s;
@@ -366,12 +448,10 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, const RenderTarge
 
     if (lane == 0) {
       s_nv[s] = nv;
-      {  // colour - background per channel, three signed 10-bit fields
-        const int dr = (int)(col & 255u) - (int)(rd.bg & 255u);
-        const int dg = (int)((col >> 8) & 255u) - (int)((rd.bg >> 8) & 255u);
-        const int db = (int)((col >> 16) & 255u) - (int)((rd.bg >> 16) & 255u);
-        s_dr[s] = (dr & 1023) | ((dg & 1023) << 10) | ((db & 1023) << 20);
-      }
+      // colour - background per channel
+      s_dcol[s] = make_int4((int)(col & 255u) - (int)(rd.bg & 255u),
+                            (int)((col >> 8) & 255u) - (int)((rd.bg >> 8) & 255u),
+                            (int)((col >> 16) & 255u) - (int)((rd.bg >> 16) & 255u), 0);
       s_nh[s] = __popc(hmask);
       s_hasov[s] = any_join ? 1 : 0;
       s_pymax[s] = p_ymax;
@@ -389,21 +469,25 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, const RenderTarge
       }
       s_region[s * 4 + 0] = yo0; s_region[s * 4 + 1] = yo1;
       s_region[s * 4 + 2] = xo0; s_region[s * 4 + 3] = xo1;
-      // tile plan: equal row blocks whose canvas rows (<= ny*aa + 32) fit the H buffer, equal
-      // column blocks of at most TILE_X_MAX (columns need no halo, rows do)
+      // tile plan: the blocks of eight output rows the region touches, in equal groups of at
+      // most TILE_BLOCKS; equal column blocks of at most TILE_X_MAX (columns need no halo)
       int pny = 1, pnx = 1;
       if (yo1 >= yo0 && xo1 >= xo0) {
-        // regions are at most band_rows x W outputs; the reciprocal table covers divisors <= 64
-        const int rh = yo1 - yo0 + 1, rw = xo1 - xo0 + 1;
-        const int ny_cap = rd.ny_cap;  // (ny-1)*aa + len <= HT_ROWS
-        const int nty = ny_cap <= 64 ? div20(rh + ny_cap - 1, ny_cap) : 1;
-        pny = nty <= 64 ? div20(rh + nty - 1, nty) : (rh + nty - 1) / nty;
-        const int ntx = div20(rw + TILE_X_MAX - 1, TILE_X_MAX);
+        const int nb = (yo1 >> 3) - (yo0 >> 3) + 1, rw = xo1 - xo0 + 1;  // nb <= 8: bands have <= 64 rows
+        const int nty = div20(nb + TILE_BLOCKS - 1, TILE_BLOCKS);
+        pny = div20(nb + nty - 1, nty);
+        const int ntx = div20(rw + TILE_X_MAX - 1, TILE_X_MAX);  // rw <= 4096
         pnx = ntx <= 64 ? div20(rw + ntx - 1, ntx) : (rw + ntx - 1) / ntx;
       }
       s_pny[s] = pny; s_pnx[s] = pnx;
       s_pinvh[s] = (int)c_inv20[(pnx + H_NC - 1) / H_NC];
     }
+  }
+  // the previous frame's write-out must have read the staged frame before phase B reuses the
+  // scratch area it lives in
+  if (tid == 0 && copy_pending) {
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    copy_pending = false;
   }
   __syncthreads();
   SWB_MARK(3);
@@ -542,7 +626,7 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, const RenderTarge
             int gap_end = b;
             int next_cursor = b + 1;
             if (i < nseg) {
-              const int xs = (int)(seg[i] & 0xFFFu), xe = (int)((seg[i] >> 12) & 0xFFFu);
+              const int xs = (int)(seg[i] & 0xFFFu), xe = (int)((seg[i] >> 12) & 0x1FFFu) - 1;
               if (xe < cursor) continue;
               gap_end = min(b, xs - 1);
               next_cursor = xe + 1;
@@ -550,7 +634,7 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, const RenderTarge
             if (cursor <= gap_end) {
               if (nseg < SEGCAP) {
                 for (int m = nseg; m > i; --m) seg[m] = seg[m - 1];
-                seg[i] = (uint32_t)cursor | ((uint32_t)gap_end << 12) | ((uint32_t)s << 24);
+                seg[i] = (uint32_t)cursor | ((uint32_t)(gap_end + 1) << 12) | ((uint32_t)s << 25);
                 ++nseg;
                 ++i;  // the segment we compared against moved one slot up
               } else {
@@ -591,167 +675,197 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, const RenderTarge
   __syncthreads();
   SWB_MARK(7);
 
-  // ---- phase C: per sprite region, in tiles sized to the H buffer -----------------------
-  // A region of h x w outputs is cut into ceil(h/32) row blocks and, per row block, into as
-  // few equal column blocks as fit HT_ITEMS H values (columns need no halo, rows do).
+  // ---- phase C: per sprite region, in tiles of <= TILE_BLOCKS blocks of eight output rows
+  // x <= TILE_X_MAX columns.  Blocks are aligned to multiples of eight output rows of the
+  // frame, so that a block's tap matrix is one of a few classes (rd.v_blk_cls); outputs of a
+  // block outside the region are computed from whatever the H tile holds and not stored.
   const int bg_r = rd.bg & 255u, bg_g = (rd.bg >> 8) & 255u, bg_b = (rd.bg >> 16) & 255u;
-  const uint32_t bg_h = (uint32_t)bg_r | ((uint32_t)bg_g << 10) | ((uint32_t)bg_b << 20);
+  const uint32_t sm0 = render_smem_base();
+  const uint32_t ht0 = sm0 + (uint32_t)L.off_scratch, sm_frame = sm0 + (uint32_t)L.off_frame;
+  const uint32_t sm_prefix = sm0 + (uint32_t)L.off_prefix, sm_nseg = sm0 + (uint32_t)L.off_nseg;
+  const uint32_t sm_segs = sm0 + (uint32_t)L.off_segs, sm_rel = sm0 + (uint32_t)L.off_rel;
+  // V pass: this thread's row of the H tile (16 (warp & 3) + lane / 4) and its byte offset
+  // there (k words lane % 4 ...), fixed for the whole kernel
+  const int v_n0 = 16 * (warp & 3) + (lane >> 2);
+  const uint32_t v_aoff = (uint32_t)(v_n0 * HT_ROWW + (lane & 3)) * 4u;
+  const int row_bytes = rd.W * 3;
   for (int s = 0; s < S; ++s) {
     const int ryo0 = s_region[s * 4 + 0], ryo1 = s_region[s * 4 + 1];
     const int rxo0 = s_region[s * 4 + 2], rxo1 = s_region[s * 4 + 3];
     if (ryo1 < ryo0 || rxo1 < rxo0) continue;
-    const int ny_blk = s_pny[s], nx_blk = s_pnx[s];
-    for (int ty0 = ryo0; ty0 <= ryo1; ty0 += ny_blk) {
-      const int ny = min(ny_blk, ryo1 - ty0 + 1);
-      const uint32_t yw0 = s_ywin[ty0 - yo_b0], yw1 = s_ywin[ty0 + ny - 1 - yo_b0];
-      const int tr0 = (int)(int16_t)(yw0 & 0xFFFFu);
-      const int tr1 = (int)(int16_t)(yw1 & 0xFFFFu) + (int)((yw1 >> 16) & 0xFFu);  // exclusive
-      const int nr = tr1 - tr0;
+    const int nb_blk = s_pny[s], nx_blk = s_pnx[s];
+    const int rb1 = ryo1 >> 3;
+    for (int tb0 = ryo0 >> 3; tb0 <= rb1; tb0 += nb_blk) {
+      const int tb1 = min(tb0 + nb_blk - 1, rb1);
+      // outputs of the region inside this tile, the canvas rows their windows span, and the
+      // tile's row origin: the 4-aligned first row of its first block
+      const int yo_first = max(ryo0, tb0 << 3), yo_last = min(ryo1, (tb1 << 3) + 7);
+      const int tr0 = (int)(int16_t)(s_ywin[(tb0 << 3) - yo_b0] & 0xFFFFu) & ~3;
+      const uint32_t ywl = s_ywin[yo_last - yo_b0];
+      const int q0 = ((int)(int16_t)(s_ywin[yo_first - yo_b0] & 0xFFFFu) - tr0) >> 2;
+      const int q1 = ((int)(int16_t)(ywl & 0xFFFFu) + (int)((ywl >> 16) & 0xFFu) - 1 - tr0) >> 2;
       for (int tx0 = rxo0; tx0 <= rxo1; tx0 += nx_blk) {
         const int nx = min(nx_blk, rxo1 - tx0 + 1);
-        // ---- H pass: a thread owns NC columns (c0, c0 + cs, ...) and strides over the canvas
-        // rows, so the window start/length and tap prefix table are loop invariants and the
-        // row's segment records are decoded once for all its columns ----
+        // ---- which segments can this tile see?  A row's list holds the visible segments of the
+        // whole canvas row, sorted by x; the ones inside [x4lo, x4hi) (the tile's tap windows,
+        // in bytes of the prefix table) are contiguous.  One thread per canvas row of the tile
+        // finds them: first index | count << 8, so that the H pass loops over those only ----
+        const uint32_t xwa = s_xwin[tx0], xwb = s_xwin[tx0 + nx - 1];
+        const int x4lo = (int)(int16_t)(xwa & 0xFFFFu) << 2;
+        const int x4hi = ((int)(int16_t)(xwb & 0xFFFFu) + (int)((xwb >> 16) & 0xFFu)) << 2;
+        if (tid < ((q1 - q0 + 1) << 2)) {
+          const int rel = tr0 - row_b0 + (q0 << 2) + tid;  // band-relative canvas row (the lists are zero past n_rows)
+          const int n = (int)lds_u8(sm_nseg + (uint32_t)rel);
+          uint32_t seg_addr = sm_segs + (uint32_t)(rel * SEGCAP) * 4u;
+          int k = 0;
+          while (k < n && (int)((lds_u32(seg_addr) >> 10) & 0x7FFCu) <= x4lo) { ++k; seg_addr += 4u; }
+          const int first = k;
+          while (k < n && (int)((lds_u32(seg_addr) << 2) & 0x3FFCu) < x4hi) { ++k; seg_addr += 4u; }
+          asm volatile("st.shared.u16 [%0], %1;" : : "r"(sm_rel + 2u * (uint32_t)tid), "r"((uint32_t)first | ((uint32_t)(k - first) << 8)) : "memory");
+        }
+        __syncthreads();
+        // ---- H pass: a thread owns NC columns (c0, c0 + cs) of a quad of canvas rows and
+        // strides over the quads, so the window start/length and tap prefix table are loop
+        // invariants and a row's segment records are decoded once for its columns; the four
+        // uint8 results of a (column, channel) leave as one word ----
         {
-          const int cs = (nx + H_NC - 1) / H_NC;  // column stride = threads per canvas row
+          const int cs = (nx + H_NC - 1) / H_NC;  // column stride = threads per quad
           const uint32_t inv_cs = nx == nx_blk ? (uint32_t)s_pinvh[s] : c_inv20[cs];
-          const int rgroup = (int)(((uint32_t)tid * inv_cs) >> 20);  // tid / cs
-          const int c0 = tid - rgroup * cs;
-          const int rstride = (int)(((uint32_t)R_THREADS * inv_cs) >> 20);  // row groups per pass
-          if (rgroup < rstride) {
-            const uint32_t prefix0 = (uint32_t)__cvta_generic_to_shared(s_prefix);
-            int xmin[H_NC], len[H_NC], kk[H_NC];
-            uint32_t pp[H_NC];
-            bool on[H_NC];
+          const int qgroup = (int)(((uint32_t)tid * inv_cs) >> 20);  // tid / cs
+          const int c0 = tid - qgroup * cs;
+          const int qstride = (int)(((uint32_t)R_THREADS * inv_cs) >> 20);  // quads per pass
+          if (qgroup < qstride) {
+            // per column: prefix-table window [plo, phi] (shared byte addresses) and the offset
+            // that maps 4*x to the address of P[x - xmin]; clamping the sum to [plo, phi] is
+            // the clamp of x to the tap window
+            int poff[H_NC], plo[H_NC], phi[H_NC], kk[H_NC];
 #pragma unroll
             for (int q = 0; q < H_NC; ++q) {
               const int c = c0 + q * cs;
-              on[q] = c < nx;
-              const uint32_t xw = s_xwin[tx0 + (on[q] ? c : c0)];
-              xmin[q] = (int)(int16_t)(xw & 0xFFFFu);
-              len[q] = (int)((xw >> 16) & 0xFFu);
-              pp[q] = prefix0 + (xw >> 24) * 33u * 4u;
-              kk[q] = lds_s32(pp[q] + ((uint32_t)len[q] << 2));  // sum of the window's taps
+              const uint32_t xw = s_xwin[tx0 + (c < nx ? c : c0)];
+              plo[q] = (int)(sm_prefix + (xw >> 24) * 33u * 4u);
+              phi[q] = plo[q] + (int)(((xw >> 16) & 0xFFu) << 2);
+              poff[q] = plo[q] - ((int)(int16_t)(xw & 0xFFFFu) << 2);
+              kk[q] = lds_s32((uint32_t)phi[q]);  // sum of the window's taps
             }
-            const uint32_t dcol_addr = (uint32_t)__cvta_generic_to_shared(s_dr);
-            // raw shared-window addresses, advanced by one row group per iteration
-            uint32_t nseg_addr = (uint32_t)__cvta_generic_to_shared(s_nseg) + (uint32_t)(tr0 + rgroup - row_b0);
-            uint32_t seg_row = (uint32_t)__cvta_generic_to_shared(s_segs) +
-                               (uint32_t)((tr0 + rgroup - row_b0) * SEGCAP) * 4u;
-            uint32_t ht_addr = (uint32_t)__cvta_generic_to_shared(s_ht) + (uint32_t)(rgroup * TILE_X_MAX + c0) * 4u;
-            const uint32_t seg_step = (uint32_t)(rstride * SEGCAP) * 4u;
-            const uint32_t ht_step = (uint32_t)(rstride * TILE_X_MAX) * 4u;
-            const uint32_t ht_col = (uint32_t)cs * 4u;
-            for (int r = rgroup; r < nr; r += rstride, nseg_addr += rstride, seg_row += seg_step, ht_addr += ht_step) {
-              const int nseg = (int)lds_u8(nseg_addr);
-              uint32_t hv[H_NC];
+            const bool on1 = c0 + cs < nx;
+            // raw shared-window addresses, advanced by one pass of quads per iteration
+            const int rel0 = tr0 - row_b0 + ((q0 + qgroup) << 2);  // first canvas row of the quad, band-relative
+            uint32_t rel_addr = sm_rel + (uint32_t)(qgroup << 3);  // four u16 per quad
+            uint32_t seg_quad = sm_segs + (uint32_t)(rel0 * SEGCAP) * 4u;
+            uint32_t ht_addr = ht0 + (uint32_t)(3 * c0 * HT_ROWW + q0 + qgroup) * 4u;
+            const uint32_t seg_row_step = (uint32_t)SEGCAP * 4u;
+            const uint32_t seg_step = (uint32_t)(qstride * 4 * SEGCAP) * 4u;
+            const uint32_t ht_col = (uint32_t)(3 * cs * HT_ROWW) * 4u;
+            const uint32_t bgw_r = (uint32_t)bg_r * 0x01010101u, bgw_g = (uint32_t)bg_g * 0x01010101u,
+                           bgw_b = (uint32_t)bg_b * 0x01010101u;
+            for (int qq = q0 + qgroup; qq <= q1; qq += qstride, rel_addr += (uint32_t)(qstride << 3),
+                     seg_quad += seg_step, ht_addr += (uint32_t)(qstride << 2)) {
+              uint32_t rel_lo, rel_hi;  // first | count << 8 of the quad's four rows
+              asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(rel_lo), "=r"(rel_hi) : "r"(rel_addr));
+              uint32_t wr[H_NC], wg[H_NC], wb[H_NC];
 #pragma unroll
-              for (int q = 0; q < H_NC; ++q) hv[q] = bg_h;
-              if (nseg) {
-                uint32_t seg_addr = seg_row;
-                int ar[H_NC], ag[H_NC], ab[H_NC];
-#pragma unroll
-                for (int q = 0; q < H_NC; ++q) {
-                  ar[q] = bg_r * kk[q] + (1 << 21);
-                  ag[q] = bg_g * kk[q] + (1 << 21);
-                  ab[q] = bg_b * kk[q] + (1 << 21);
-                }
-                int j = nseg;
+              for (int q = 0; q < H_NC; ++q) { wr[q] = bgw_r; wg[q] = bgw_g; wb[q] = bgw_b; }
+              if ((rel_lo | rel_hi) & 0xFF00FF00u) {
+                uint32_t seg_addr0 = seg_quad;
 #pragma unroll 1
-                do {
-                  const uint32_t w = (uint32_t)lds_s32(seg_addr);
-                  seg_addr += 4u;
-                  const int xs = (int)(w & 0xFFFu), xe1 = (int)((w >> 12) & 0xFFFu) + 1;
-                  const int d = lds_s32(dcol_addr + ((w >> 24) << 2));
-                  const int dr = (d << 22) >> 22, dg = (d << 12) >> 22, db = (d << 2) >> 22;
+                for (int i = 0; i < 4; ++i, seg_addr0 += seg_row_step) {
+                  const uint32_t fc = (i & 2 ? rel_hi : rel_lo) >> ((i & 1) << 4);
+                  int j = (int)((fc >> 8) & 255u);
+                  if (!j) continue;
+                  uint32_t seg_addr = seg_addr0 + ((fc & 255u) << 2);
+                  int ar[H_NC], ag[H_NC], ab[H_NC];
 #pragma unroll
                   for (int q = 0; q < H_NC; ++q) {
-                    const int a = min(max(xs - xmin[q], 0), len[q]), b = min(max(xe1 - xmin[q], 0), len[q]);
-                    const int wt = lds_s32(pp[q] + ((uint32_t)b << 2)) - lds_s32(pp[q] + ((uint32_t)a << 2));
-                    ar[q] += dr * wt; ag[q] += dg * wt; ab[q] += db * wt;
+                    ar[q] = bg_r * kk[q] + (1 << 21);
+                    ag[q] = bg_g * kk[q] + (1 << 21);
+                    ab[q] = bg_b * kk[q] + (1 << 21);
                   }
-                } while (--j);
+#pragma unroll 1
+                  do {
+                    const uint32_t w = lds_u32(seg_addr);
+                    seg_addr += 4u;
+                    const int xs4 = (int)((w << 2) & 0x3FFCu), xe4 = (int)((w >> 10) & 0x7FFCu);  // 4*xs, 4*(xe+1)
+                    const int4 d = lds_v4(sm0 + ((w >> 21) & 0x7F0u));  // colour - background of the segment's sprite
 #pragma unroll
-                for (int q = 0; q < H_NC; ++q)
-                  hv[q] = clip8_q22(ar[q]) | (clip8_q22(ag[q]) << 10) | (clip8_q22(ab[q]) << 20);
+                    for (int q = 0; q < H_NC; ++q) {
+                      const int a = min(max(xs4 + poff[q], plo[q]), phi[q]);
+                      const int b = min(max(xe4 + poff[q], plo[q]), phi[q]);
+                      const int wt = lds_s32((uint32_t)b) - lds_s32((uint32_t)a);
+                      ar[q] += d.x * wt; ag[q] += d.y * wt; ab[q] += d.z * wt;
+                    }
+                  } while (--j);
+                  // byte i of the words <- clip8 (Pillow's uint8 intermediate)
+                  const uint32_t psel = c_prmt_insert[i];
+#pragma unroll
+                  for (int q = 0; q < H_NC; ++q) {
+                    wr[q] = prmt(wr[q], sat_u8_q22(ar[q]), psel);
+                    wg[q] = prmt(wg[q], sat_u8_q22(ag[q]), psel);
+                    wb[q] = prmt(wb[q], sat_u8_q22(ab[q]), psel);
+                  }
+                }
               }
-#pragma unroll
-              for (int q = 0; q < H_NC; ++q)
-                if (on[q]) sts_u32(ht_addr + (uint32_t)q * ht_col, hv[q]);
+              sts_u32(ht_addr, wr[0]);
+              sts_u32(ht_addr + HT_ROWW * 4u, wg[0]);
+              sts_u32(ht_addr + 2u * HT_ROWW * 4u, wb[0]);
+              if (on1) {
+                sts_u32(ht_addr + ht_col, wr[1]);
+                sts_u32(ht_addr + ht_col + HT_ROWW * 4u, wg[1]);
+                sts_u32(ht_addr + ht_col + 2u * HT_ROWW * 4u, wb[1]);
+              }
             }
           }
         }
         __syncthreads();
         SWB_MARK(8);
-        // ---- V pass: item = (output row ly, column c).  Consecutive interior rows start 5
-        // canvas rows = 100 words = 4 banks apart in the H tile, so a warp takes 16 columns of
-        // two output rows four apart (16 banks apart): its 32 loads of one tap hit 32 banks.
-        // Rows go in blocks of eight, (j, j + 4); a last block of <= 4 rows pairs (j, j + h);
-        // columns past 16 (at most four) go as warps of 8 rows x 4 columns ----
-        const int nb8 = ny >> 3, m8 = ny & 7;
-        const int hstep = m8 > 4 ? 4 : ((m8 + 1) >> 1);
-        const int n_pair = 4 * nb8 + hstep;
-        const int n_chunk = n_pair + (nx > 16 ? ((ny + 7) >> 3) : 0);
-        for (int chunk = warp; chunk < n_chunk; chunk += NWARP) {
-          int ly, c;
-          if (chunk < n_pair) {
-            const int blk = chunk >> 2;
-            ly = (blk << 3) + (chunk & 3) + ((lane >> 4) ? (blk < nb8 ? 4 : hstep) : 0);
-            c = lane & 15;
-          } else {
-            ly = ((chunk - n_pair) << 3) + (lane >> 2);
-            c = 16 + (lane & 3);
-          }
-          if (ly >= ny || c >= nx) continue;
-          const int yo = ty0 + ly;
-          const uint32_t yw = s_ywin[yo - yo_b0];
-          const int rbase = (int)(int16_t)(yw & 0xFFFFu) - tr0;
-          const int cls = (int)(yw >> 24);
-          int ar = 1 << 21, ag = 1 << 21, ab = 1 << 21;
-          const uint32_t *col_ht = s_ht + rbase * TILE_X_MAX + c;
-          if (cls == rd.a5_cls) {
-            // interior rows of a 5x reduction: taps (k, 28-k) pair up, 4/9/19/24/29 are zero,
-            // 14 is the centre -> immediate load offsets, coefficients from the constant bank
-            constexpr int A5[12] = {0, 1, 2, 3, 5, 6, 7, 8, 10, 11, 12, 13};
+        // ---- V pass on the tensor pipe: a warp takes 16 (column, channel) rows of the H tile x
+        // one block of eight output rows: A = H values (16 x 32 canvas rows per k-step, uint8),
+        // B = the block's taps as three int8 limbs (fragments prebuilt on the host), three
+        // int32 accumulators recombined as d0 + 2^8 d1 + 2^16 d2 (+ 2^21, >> 22, clip8) ----
+        {
+          // warp w owns row tile mt = w & 3 (16 (column, channel) rows) for the whole kernel and
+          // block w >> 2 of the tile; warps 0..3 also take a third block
+          const int nks = rd.v_nks;
+          const int n3 = 3 * nx;
+          const bool pn0 = v_n0 < n3, pn1 = v_n0 + 8 < n3;
+          if (16 * (warp & 3) < n3) {  // warp-uniform (mma.sync needs the whole warp); rows past n3 are not stored
+#pragma unroll 1
+            for (int jb = warp >> 2; jb <= tb1 - tb0; jb += 2) {
+              const int yo_blk = (tb0 + jb) << 3;
+              // k origin of the block inside the tile, in words of four canvas rows
+              const int kw = (((int)(int16_t)(s_ywin[yo_blk - yo_b0] & 0xFFFFu) & ~3) - tr0) >> 2;
+              const uint32_t cls = __ldg(rd.v_blk_cls + (yo_blk >> 3));
+              const uint2 *cf = rd.v_frag + (cls * (uint32_t)nks * 96u + (uint32_t)lane);
+              const uint32_t a_addr = ht0 + v_aoff + (uint32_t)kw * 4u;
+              int d0[4] = {1 << 21, 1 << 21, 1 << 21, 1 << 21}, d1[4] = {0, 0, 0, 0}, d2[4] = {0, 0, 0, 0};
 #pragma unroll
-            for (int k = 0; k < 12; ++k) {
-              const int kk = rd.a5_coef[k];
-              // two taps of equal coefficient: the 10-bit fields hold sums up to 510
-              const uint32_t t = col_ht[A5[k] * TILE_X_MAX] + col_ht[(28 - A5[k]) * TILE_X_MAX];
-              ar += (int)(t & 1023u) * kk;
-              ag += (int)((t >> 10) & 1023u) * kk;
-              ab += (int)(t >> 20) * kk;
-            }
-            const int kk = rd.a5_coef[12];
-            const uint32_t t = col_ht[14 * TILE_X_MAX];
-            ar += (int)(t & 1023u) * kk;
-            ag += (int)((t >> 10) & 1023u) * kk;
-            ab += (int)(t >> 20) * kk;
-          } else {
-            const int32_t *prog = rd.ay.program + cls * PROG_STRIDE;  // global, read-only
-            const int np = __ldg(prog), ns = __ldg(prog + 1) & 0xFFFF;
-            const int2 *pp = reinterpret_cast<const int2 *>(prog + 2);
-            const int2 *ps = reinterpret_cast<const int2 *>(prog + 2 + 2 * 16);
-            for (int k = 0; k < np; ++k) {
-              const int2 pk = __ldg(pp + k);  // (row a | row b << 8, coefficient)
-              const uint32_t t = col_ht[(pk.x & 255) * TILE_X_MAX] + col_ht[(pk.x >> 8) * TILE_X_MAX];
-              ar += (int)(t & 1023u) * pk.y;
-              ag += (int)((t >> 10) & 1023u) * pk.y;
-              ab += (int)(t >> 20) * pk.y;
-            }
-            for (int k = 0; k < ns; ++k) {
-              const int2 pk = __ldg(ps + k);
-              const uint32_t t = col_ht[pk.x * TILE_X_MAX];
-              ar += (int)(t & 1023u) * pk.y;
-              ag += (int)((t >> 10) & 1023u) * pk.y;
-              ab += (int)(t >> 20) * pk.y;
+              for (int ks = 0; ks < 3; ++ks) {  // v_nks <= 3
+                if (ks < nks) {
+                  uint32_t a[4];
+                  a[0] = lds_u32(a_addr + 32u * ks);
+                  a[1] = lds_u32(a_addr + 32u * ks + 8u * HT_ROWW * 4u);
+                  a[2] = lds_u32(a_addr + 32u * ks + 16u);
+                  a[3] = lds_u32(a_addr + 32u * ks + 8u * HT_ROWW * 4u + 16u);
+                  const uint2 b0 = __ldg(cf + (ks * 3 + 0) * 32);
+                  const uint2 b1 = __ldg(cf + (ks * 3 + 1) * 32);
+                  const uint2 b2 = __ldg(cf + (ks * 3 + 2) * 32);
+                  mma_u8s8(d0, a, b0);
+                  mma_u8s8(d1, a, b1);
+                  mma_u8s8(d2, a, b2);
+                }
+              }
+              // accumulator r: row n = n0 (+8 for r >= 2), output row yo0 + (r & 1).  Staged in
+              // destination order: output row yo is row H-1-yo of the frame (np.flipud)
+              const int yo0 = yo_blk + 2 * (lane & 3);
+              const uint32_t f_addr = sm_frame + (uint32_t)((yo_b1 - 1 - yo0) * row_bytes + 3 * tx0 + v_n0);
+              const bool py0 = (unsigned)(yo0 - yo_first) <= (unsigned)(yo_last - yo_first);
+              const bool py1 = (unsigned)(yo0 + 1 - yo_first) <= (unsigned)(yo_last - yo_first);
+              if (pn0 && py0) sts_u8(f_addr, sat_u8_q22(d0[0] + (d1[0] << 8) + (d2[0] << 16)));
+              if (pn0 && py1) sts_u8(f_addr - (uint32_t)row_bytes, sat_u8_q22(d0[1] + (d1[1] << 8) + (d2[1] << 16)));
+              if (pn1 && py0) sts_u8(f_addr + 8u, sat_u8_q22(d0[2] + (d1[2] << 8) + (d2[2] << 16)));
+              if (pn1 && py1) sts_u8(f_addr - (uint32_t)row_bytes + 8u, sat_u8_q22(d0[3] + (d1[3] << 8) + (d2[3] << 16)));
             }
           }
-          // staged in destination order: output row yo is row H-1-yo of the frame (np.flipud)
-          uint8_t *px = s_frame + ((size_t)(yo_b1 - 1 - yo) * rd.W + tx0 + c) * 3;
-          px[0] = (uint8_t)clip8_q22(ar);
-          px[1] = (uint8_t)clip8_q22(ag);
-          px[2] = (uint8_t)clip8_q22(ab);
         }
         __syncthreads();
         SWB_MARK(9);
@@ -761,11 +875,11 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, const RenderTarge
 
   // ---- phase D: staged frame -> HBM.  The frame is staged in destination order (rows already
   // flipped, np.flipud), so the band is one contiguous block: one thread hands it to the
-  // bulk-copy engine (TMA, cp.async.bulk shared -> global), once per target.  With several
-  // targets the same block also goes to the other ranks' buffers over NVLink peer memory:
-  // the frame gather of the multi-GPU path is issued by the kernel that produced the frame
-  // and costs it one instruction per rank -------------------------------------------------
-  const int row_bytes = rd.W * 3;
+  // bulk-copy engine (TMA, cp.async.bulk shared -> global), once per target; the engine reads
+  // the staged frame while the CTA sets up its next frame (the wait is at the end of phase A).
+  // With several targets the same block also goes to the other ranks' buffers over NVLink
+  // peer memory: the frame gather of the multi-GPU path is issued by the kernel that produced
+  // the frame and costs it one instruction per rank ----------------------------------------
   const int n_bytes = n_yo * row_bytes;
   const size_t band_off = (size_t)(targets.env_offset + e) * rd.H * row_bytes + (size_t)(rd.H - yo_b1) * row_bytes;
   if ((n_bytes & 15) == 0 && (band_off & 15) == 0) {
@@ -774,11 +888,11 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, const RenderTarge
     __syncthreads();
     if (tid == 0) {
       const uint32_t src = (uint32_t)__cvta_generic_to_shared(s_frame);
-      // peers in an order rotated by rank and CTA, so that at any moment the ranks' copies are
+      // peers in an order rotated by rank and frame, so that at any moment the ranks' copies are
       // spread over all receivers instead of all hitting rank 0 first, then rank 1, ...
       int t = 0;
-      if (kPeers) {  // (self + 1 + blockIdx.x) mod n without a division (n <= 8)
-        t = targets.self + 1 + (int)(blockIdx.x & 7u);
+      if (kPeers) {  // (self + 1 + item) mod n without a division (n <= 8)
+        t = targets.self + 1 + (int)((unsigned)item & 7u);
         while (t >= targets.n) t -= targets.n;
       }
       for (int i = 0; i < (kPeers ? targets.n : 1); ++i) {
@@ -787,8 +901,7 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, const RenderTarge
         if (kPeers && ++t == targets.n) t = 0;
       }
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      // the CTA's shared memory must stay until the engine has read it
-      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      copy_pending = true;
     }
   } else {
     for (int i = tid; i < n_bytes; i += R_THREADS) {
@@ -801,6 +914,9 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, const RenderTarge
   // several bands of one env may race here, but they all OR in the same bit
   if (tid == 0 && s_overflow) st.render_status[e] |= (uint8_t)SWB_ENV_SPAN_OVERFLOW;
   SWB_MARK(10);
+  }  // item loop
+  // the CTA's shared memory must stay until the engine has read it
+  if (tid == 0 && copy_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 }  // namespace swb

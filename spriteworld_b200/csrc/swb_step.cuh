@@ -482,6 +482,7 @@ step_kernel(DevState st, const StepCfg *__restrict__ step_cfg, const void *__res
       out.reward[e] = __dadd_rn(cost, tr);  // :101
     }
     st.cursor[e] = cursor;
+    if (resetting) st.scene_serial[e] += 1;  // monotonic: the host's refill bookkeeping reads it
     st.step_count[e] = count;
     st.reset_next[e] = (step_type == SWB_STEP_LAST) ? 1 : 0;
     out.step_type[e] = (int8_t)step_type;

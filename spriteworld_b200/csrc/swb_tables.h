@@ -5,9 +5,9 @@
 // renderers/pil_renderer.py:84): support 3*scale, window [int(c-s+.5), int(c+s+.5)),
 // taps normalised in double and quantised to 22-bit fixed point.  On top of the raw taps
 // the kernel wants: a class id per output (outputs with identical tap vectors share one
-// table), prefix sums per class (horizontal pass over piecewise-constant rows), a
-// paired-tap program per class (vertical pass: equal coefficients share a multiply) and
-// the inverse maps "input index -> first/last output whose window contains it".
+// table), prefix sums per class (horizontal pass over piecewise-constant rows), the
+// inverse maps "input index -> first/last output whose window contains it" and, for the
+// vertical pass, the tap matrix of every block of eight outputs as tensor-core fragments.
 #pragma once
 #include <algorithm>
 #include <array>
@@ -28,7 +28,6 @@ struct AxisHost {
   std::vector<int16_t> win_min;
   std::vector<uint8_t> win_len, win_cls;
   std::vector<int32_t> prefix;   // [n_cls][33]
-  std::vector<int32_t> program;  // [n_cls][PROG_STRIDE]
   std::vector<int16_t> first_out, last_out;
   std::vector<std::vector<int32_t>> taps;  // per output, for tests
 };
@@ -113,7 +112,6 @@ inline bool build_axis(int n_in, int n_out, AxisHost *ax, std::string *err) {
   }
   ax->n_cls = (int)cls.size();
   ax->prefix.assign((size_t)ax->n_cls * 33, 0);
-  ax->program.assign((size_t)ax->n_cls * PROG_STRIDE, 0);
   for (const auto &kv : cls) {
     const std::vector<int32_t> &t = kv.first;
     int32_t *P = ax->prefix.data() + (size_t)kv.second * 33;
@@ -122,39 +120,6 @@ inline bool build_axis(int n_in, int n_out, AxisHost *ax, std::string *err) {
       P[i] = run;
       if (i < (int)t.size()) run += t[i];
     }
-    // paired-tap program: taps with equal non-zero coefficient are added before the multiply.
-    // Pairs are emitted in ascending order of their first tap.
-    int32_t *prog = ax->program.data() + (size_t)kv.second * PROG_STRIDE;
-    std::map<int32_t, std::vector<int>> by_coef;
-    for (int i = 0; i < (int)t.size(); ++i)
-      if (t[i] != 0) by_coef[t[i]].push_back(i);
-    std::vector<std::array<int32_t, 3>> pair_list;  // a, b, coefficient
-    std::vector<std::array<int32_t, 2>> single_list;
-    for (const auto &bc : by_coef) {
-      const std::vector<int> &idx = bc.second;
-      size_t i = 0;
-      for (; i + 1 < idx.size() && pair_list.size() < 16; i += 2) pair_list.push_back({idx[i], idx[i + 1], bc.first});
-      for (; i < idx.size(); ++i) single_list.push_back({idx[i], bc.first});
-    }
-    std::sort(pair_list.begin(), pair_list.end());
-    std::sort(single_list.begin(), single_list.end());
-    int32_t *pairs = prog + 2, *singles = prog + 2 + 2 * 16;
-    for (size_t i = 0; i < pair_list.size(); ++i) {
-      pairs[2 * i] = pair_list[i][0] | (pair_list[i][1] << 8);
-      pairs[2 * i + 1] = pair_list[i][2];
-    }
-    for (size_t i = 0; i < single_list.size(); ++i) {
-      singles[2 * i] = single_list[i][0];
-      singles[2 * i + 1] = single_list[i][1];
-    }
-    // the interior vector of a 5x LANCZOS reduction: taps k and 28-k are
-    // equal, taps 4, 9, 19, 24, 29 are zero, tap 14 is the centre.  The kernel has an
-    // unrolled path with immediate offsets for exactly this shape (flag in bit 16 of ns).
-    static const int kA5[12] = {0, 1, 2, 3, 5, 6, 7, 8, 10, 11, 12, 13};
-    bool a5 = pair_list.size() == 12 && single_list.size() == 1 && single_list[0][0] == 14;
-    for (int i = 0; a5 && i < 12; ++i) a5 = pair_list[i][0] == kA5[i] && pair_list[i][1] == 28 - kA5[i];
-    prog[0] = (int32_t)pair_list.size();
-    prog[1] = (int32_t)single_list.size() | (a5 ? (1 << 16) : 0);
   }
   // inverse maps
   ax->first_out.assign(n_in, (int16_t)(n_out - 1));
@@ -178,6 +143,94 @@ inline bool build_axis(int n_in, int n_out, AxisHost *ax, std::string *err) {
       ax->first_out[i] = 1;
       ax->last_out[i] = 0;
     }
+  return true;
+}
+
+// Vertical pass as a banded integer contraction on the tensor pipe.
+//
+// out[yo][n] = clip8((2^21 + sum_r K[yo][r] * Hval[r][n]) >> 22), Hval uint8, K the 22-bit taps
+// (Pillow ImagingResampleVertical_8bpc).  The render kernel evaluates it per block of eight
+// output rows with mma.sync.m16n8k32 (A = 16 H columns x 32 canvas rows of uint8, B = 32
+// canvas rows x 8 output rows of int8, int32 accumulators): K = l0 + 2^8 l1 + 2^16 l2 with
+// l0, l1 in [-128, 127], one MMA per limb, recombined with shifts -- exact in int32 because
+// the true sum is below 2^31.  A block's canvas rows are addressed from the 4-aligned row
+// o = win_min[8b] & ~3 (four consecutive canvas rows share one 32-bit word of the H tile).
+// Blocks with the same matrix share a class; per class the fragments are stored in the
+// register layout of the instruction: lane (g = lane/4, t = lane%4) holds for output row g
+// b0 = limb(K[8b+g][o + 32ks + 4t + 0..3]) and b1 = the same 16 rows further.
+struct VFragHost {
+  int nks = 1, n_cls = 0;
+  std::vector<uint8_t> blk_cls;   // [ceil(n_out/8)]
+  std::vector<uint32_t> frag;     // [n_cls][nks][3][32][2]
+};
+
+inline bool build_vfrag(const AxisHost &ay, VFragHost *vf, std::string *err) {
+  const int n_blk = (ay.n_out + 7) / 8;
+  auto coef = [&](int yo, int r) -> int32_t {
+    if (yo >= ay.n_out) return 0;
+    const int i = r - ay.win_min[yo];
+    return (i >= 0 && i < (int)ay.win_len[yo]) ? ay.taps[yo][i] : 0;
+  };
+  int nks = 1;
+  for (int b = 0; b < n_blk; ++b) {
+    const int o = ay.win_min[8 * b] & ~3;
+    int end = o + 1;
+    for (int j = 0; j < 8 && 8 * b + j < ay.n_out; ++j) {
+      const int yo = 8 * b + j;
+      int last = (int)ay.win_len[yo] - 1;  // trailing zero taps need no k-step (5x LANCZOS: tap 29)
+      while (last > 0 && ay.taps[yo][last] == 0) --last;
+      end = std::max(end, ay.win_min[yo] + last + 1);
+    }
+    nks = std::max(nks, (end - o + 31) / 32);
+  }
+  vf->nks = nks;
+  vf->blk_cls.assign(n_blk, 0);
+  std::map<std::vector<uint32_t>, int> classes;
+  std::vector<std::vector<uint32_t>> ordered;
+  for (int b = 0; b < n_blk; ++b) {
+    const int o = ay.win_min[8 * b] & ~3;
+    std::vector<uint32_t> f((size_t)nks * 3 * 32 * 2, 0u);
+    for (int ks = 0; ks < nks; ++ks)
+      for (int lane = 0; lane < 32; ++lane) {
+        const int g = lane >> 2, t = lane & 3;
+        for (int half = 0; half < 2; ++half) {
+          uint32_t w[3] = {0u, 0u, 0u};
+          for (int i = 0; i < 4; ++i) {
+            const int32_t k = coef(8 * b + g, o + 32 * ks + 16 * half + 4 * t + i);
+            const int32_t l0 = ((k + 128) & 255) - 128;
+            const int32_t k1 = (k - l0) >> 8;
+            const int32_t l1 = ((k1 + 128) & 255) - 128;
+            const int32_t l2 = (k1 - l1) >> 8;
+            if (l2 < -128 || l2 > 127) {
+              *err = "resampling coefficient does not fit three signed 8-bit limbs";
+              return false;
+            }
+            w[0] |= (uint32_t)(uint8_t)(int8_t)l0 << (8 * i);
+            w[1] |= (uint32_t)(uint8_t)(int8_t)l1 << (8 * i);
+            w[2] |= (uint32_t)(uint8_t)(int8_t)l2 << (8 * i);
+          }
+          for (int limb = 0; limb < 3; ++limb)
+            f[(((size_t)ks * 3 + limb) * 32 + lane) * 2 + half] = w[limb];
+        }
+      }
+    auto it = classes.find(f);
+    int id;
+    if (it == classes.end()) {
+      id = (int)classes.size();
+      if (id > 255) {
+        *err = "more than 256 distinct vertical tap blocks";
+        return false;
+      }
+      classes.emplace(f, id);
+      ordered.push_back(f);
+    } else {
+      id = it->second;
+    }
+    vf->blk_cls[b] = (uint8_t)id;
+  }
+  vf->n_cls = (int)ordered.size();
+  vf->frag.clear();
+  for (const auto &f : ordered) vf->frag.insert(vf->frag.end(), f.begin(), f.end());
   return true;
 }
 

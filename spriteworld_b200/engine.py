@@ -35,6 +35,18 @@ class StepResult(object):
     self.status, self.frames = status, frames
 
 
+class SerialSnapshot(object):
+  """scene_serial of every env as of the steps enqueued when it was requested; `wait()` blocks
+  the calling host thread (not the step stream) until the copy has landed."""
+
+  def __init__(self, host, event):
+    self._host, self._event = host, event
+
+  def wait(self):
+    self._event.synchronize()
+    return self._host.numpy().astype(np.int64)
+
+
 class Raster(object):
   """PILRenderer(image_size=(width, height), anti_aliasing, bg_color) on the device."""
 
@@ -141,6 +153,47 @@ class Engine(object):
     ring_slots = np.ascontiguousarray(ring_slots, dtype=np.int32)
     _native.check(self._lib.swb_upload_scenes(self._h, ctypes.byref(soa), _as_ptr(env_ids),
                                               _as_ptr(ring_slots), n, self._stream()))
+
+  def scene_serial(self):
+    """Zero-copy int32 (E,) view of how many scenes each env has started (monotonic)."""
+    if getattr(self, '_serial_view', None) is None:
+      p = ctypes.c_void_p()
+      _native.check(self._lib.swb_scene_serial_pointer(self._h, ctypes.byref(p)))
+      self._serial_view = torch.as_tensor(_DevicePointer(p.value, (self.n_envs,), '<i4'),
+                                          device=self.device)
+    return self._serial_view
+
+  def side_stream(self):
+    """The engine's stream for work that must not hold up the step stream (scene refills)."""
+    if getattr(self, '_side', None) is None:
+      self._side = torch.cuda.Stream(device=self.device)
+    return self._side
+
+  def snapshot_scene_serial(self):
+    """Asynchronous device->pinned copy of scene_serial, ordered after the work enqueued so far
+    on the current stream and issued on the side stream.  Returns a SerialSnapshot."""
+    if getattr(self, '_serial_host', None) is None:
+      self._serial_host = [torch.empty(self.n_envs, dtype=torch.int32).pin_memory() for _ in range(2)]
+      self._serial_i = 0
+    side = self.side_stream()
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(self.device))
+    side.wait_event(ev)
+    host = self._serial_host[self._serial_i]
+    self._serial_i ^= 1
+    with torch.cuda.stream(side):
+      host.copy_(self.scene_serial(), non_blocking=True)
+      done = torch.cuda.Event()
+      done.record(side)
+    return SerialSnapshot(host, done)
+
+  def download_state_serial(self):
+    """scene_serial as a host array, after everything enqueued so far (synchronous)."""
+    return self.scene_serial().cpu().numpy().astype(np.int64)
+
+  def wait_event(self, event):
+    """Makes the current (step) stream wait for `event` without blocking the host."""
+    torch.cuda.current_stream(self.device).wait_event(event)
 
   def request_reset(self, mask=None):
     ptr = None

@@ -238,7 +238,15 @@ class BatchedEnvironment(object):
 
   def __init__(self, task, action_space, renderers, init_sprites, keep_in_frame=True,
                max_episode_length=1000, metadata=None, n_envs=1, n_slots=None, pool_depth=8,
-               device=0, rng=None, env_offset=0):
+               device=0, rng=None, refill=None):
+    """Args beyond the reference's Environment:
+      n_envs: environments advanced in lockstep.
+      n_slots: sprite slots per env; default: the generator's own bound (`max_sprites`), or,
+        when a user callable draws the sprite count, the largest count seen in a probe sample.
+      pool_depth: K, scenes kept per env on the device (the ring auto-resets draw from).
+      refill: 'async' (default on CUDA: a host thread samples and uploads consumed ring slots
+        over a side stream, the step stream waits only if a ring would underflow) or 'sync'.
+    """
     self._task, self._action_space = task, action_space
     self._renderers = renderers
     self._init_sprites = init_sprites
@@ -255,7 +263,13 @@ class BatchedEnvironment(object):
     self._K = max(3, int(pool_depth))
     E, K = self.n_envs, self._K
     first = self._sample(E * K)
-    slots = n_slots or max(1, int(first.count.max()))
+    slots = n_slots or getattr(init_sprites, 'max_sprites', None)
+    if not slots:
+      # the count is drawn by a user callable: size the slots from a probe sample, so that a
+      # later refill cannot meet a larger scene in the middle of a run
+      probe = self._sample(4096)
+      slots = max(1, int(first.count.max()), int(probe.count.max()))
+    slots = max(1, int(slots))
     self._engine = engine_lib.Engine(
         E, slots, K, action_space.compile(), self._nodes, constants.SHAPES,
         keep_in_frame=keep_in_frame,
@@ -269,13 +283,30 @@ class BatchedEnvironment(object):
     # to reset (environment.py:70)
     self._engine.upload_state(pos_x=batch0['x'][::K], pos_y=batch0['y'][::K],
                               cursor=np.zeros(E), step_count=np.zeros(E), reset_next=np.ones(E))
-    # ring bookkeeping in absolute scene indices (ring slot = index % K)
-    self._refilled_upto = np.full(E, K - 1, np.int64)   # newest fresh scene of each env
-    self._consumed = np.zeros(E, np.int64)              # scene each env is currently on
-    self._cursor_seen = np.zeros(E, np.int64)
-    self._steps_since_check = 0
-    # an env consumes at most one scene per two steps, so K-1 fresh scenes last 2(K-2) steps
-    self._check_every = max(1, 2 * (K - 2))
+    # Ring bookkeeping in absolute scene indices: scene a of an env lives in ring slot a % K;
+    # the device counts the scenes an env has started (scene_serial), so "serial" is the scene
+    # it is on and scenes serial+1 .. _refilled_upto are fresh.  A refill brings every env up
+    # to serial + K - 1 (the slot of the scene before the current one).
+    self._refilled_upto = np.full(E, K - 1, np.int64)
+    if refill is None:
+      refill = 'async' if self._engine.device.type == 'cuda' else 'sync'
+    if refill not in ('async', 'sync'):
+      raise ValueError("refill must be 'async' or 'sync'")
+    self._refill_mode = refill
+    # Underflow guard.  Between the snapshot a landed refill was computed from (step _safe_step,
+    # explicit resets so far _safe_resets) and step t an env can have started at most
+    # ceil((t - _safe_step) / 2) + (resets since) scenes: an auto-reset takes a LAST and a
+    # FIRST step, an explicit reset() one step.  K - 1 fresh scenes were there at the snapshot.
+    self._t = 0                    # steps enqueued
+    self._resets = 0               # explicit reset() calls
+    self._safe_step, self._safe_resets = 0, 0
+    self._period = max(1, (K - 2) // 2 if refill == 'async' else 2 * (K - 2))
+    self._inflight = None          # async: dict(snapshot step/resets, future)
+    self._worker = None
+    self._stats = dict(refills=0, scenes=0, host_seconds=0.0, blocked_seconds=0.0, blocked=0)
+    if refill == 'async':
+      import concurrent.futures
+      self._worker = concurrent.futures.ThreadPoolExecutor(1, thread_name_prefix='swb-refill')
 
   # -- scenes ----------------------------------------------------------------------------
   def _sample(self, n):
@@ -317,27 +348,91 @@ class BatchedEnvironment(object):
     out['mask'] = static[..., 0] > 0
     return out
 
-  def _refill(self):
-    """Re-samples the ring slots the device has consumed since the last check."""
-    state = self._engine.download_state()
+  def _refill_from(self, serial):
+    """Samples and uploads what brings every env's ring up to serial + K - 1.  `serial`: scene
+    each env was on at the snapshot.  Returns the number of scenes uploaded."""
     K = self._K
-    cur = state['cursor'].astype(np.int64)
-    advanced = (cur - self._cursor_seen) % K
-    self._consumed += advanced
-    self._cursor_seen = cur
-    # scenes with absolute index <= consumed are used up; keep K-1 fresh ones ahead
-    want_upto = self._consumed + (K - 1)
-    n_new = want_upto - self._refilled_upto
+    want_upto = np.asarray(serial, np.int64) + (K - 1)
+    n_new = np.maximum(want_upto - self._refilled_upto, 0)
     total = int(n_new.sum())
     if total <= 0:
-      return
+      return 0
     env_ids = np.repeat(np.arange(self.n_envs), n_new)
     # 1..n_new[e] for every env, concatenated
     offs = np.arange(total) - np.repeat(np.cumsum(n_new) - n_new, n_new) + 1
     absolute = np.repeat(self._refilled_upto, n_new) + offs
     layout = self._sample(total)
     self._upload(layout, env_ids, absolute % K)
-    self._refilled_upto = want_upto
+    self._refilled_upto = np.maximum(self._refilled_upto, want_upto)
+    return total
+
+  def _refill_job(self, snapshot):
+    """Worker thread: wait for the snapshot copy (not for the step stream), sample, pack,
+    upload over the side stream.  Returns the event after which the scenes are in the pool."""
+    import time
+    serial = snapshot.wait()
+    t0 = time.perf_counter()
+    eng = self._engine
+    torch.cuda.set_device(eng.device)
+    with torch.cuda.stream(eng.side_stream()):
+      n = self._refill_from(serial)
+      done = torch.cuda.Event()
+      done.record(eng.side_stream())
+    self._stats['host_seconds'] += time.perf_counter() - t0
+    self._stats['refills'] += 1
+    self._stats['scenes'] += n
+    return done
+
+  def _risk(self, t):
+    """Upper bound of the scenes an env can have started by step t since the last landed refill."""
+    return (t - self._safe_step + 1) // 2 + (self._resets - self._safe_resets)
+
+  def _land(self, block):
+    """Absorbs the in-flight refill if it is finished (or waits for it): the step stream waits
+    on its upload event, the guard moves to its snapshot."""
+    job = self._inflight
+    if job is None or not (block or job['future'].done()):
+      return
+    if not job['future'].done():
+      import time
+      t0 = time.perf_counter()
+      job['future'].result()
+      self._stats['blocked_seconds'] += time.perf_counter() - t0
+      self._stats['blocked'] += 1
+    self._engine.wait_event(job['future'].result())
+    self._safe_step, self._safe_resets = job['step'], job['resets']
+    self._inflight = None
+
+  def _request(self):
+    snapshot = self._engine.snapshot_scene_serial()
+    self._inflight = dict(step=self._t, resets=self._resets,
+                          future=self._worker.submit(self._refill_job, snapshot))
+
+  def _keep_ring_fresh(self):
+    """Called before a step is enqueued."""
+    K = self._K
+    if self._refill_mode == 'sync':
+      if self._t - self._safe_step >= self._period or self._risk(self._t + 1) > K - 1:
+        import time
+        t0 = time.perf_counter()
+        serial = self._engine.download_state_serial()
+        self._stats['scenes'] += self._refill_from(serial)
+        self._stats['refills'] += 1
+        self._stats['host_seconds'] += time.perf_counter() - t0
+        self._safe_step, self._safe_resets = self._t, self._resets
+      return
+    self._land(block=False)
+    if self._inflight is None and self._t - self._safe_step >= self._period:
+      self._request()
+    while self._risk(self._t + 1) > K - 1:   # this step could run a ring dry: wait for scenes
+      if self._inflight is None:
+        self._request()
+      self._land(block=True)
+
+  def refill_stats(self):
+    """Counters of the scene-ring refill: refills, scenes sampled, host seconds spent sampling
+    and packing, and how often / how long a step had to wait for scenes."""
+    return dict(self._stats, mode=self._refill_mode, pool_depth=self._K)
 
   # -- API ---------------------------------------------------------------------------------
   @property
@@ -376,10 +471,8 @@ class BatchedEnvironment(object):
 
   def step(self, actions):
     eng = self._engine
-    self._steps_since_check += 1
-    if self._steps_since_check >= self._check_every:
-      self._refill()
-      self._steps_since_check = 0
+    self._keep_ring_fresh()
+    self._t += 1
     t = self._to_device(actions)
     names = list(self._rasters)
     if names:
@@ -392,6 +485,7 @@ class BatchedEnvironment(object):
 
   def reset(self):
     """Restarts every env from its next pooled scene; returns the FIRST timestep."""
+    self._resets += 1
     self._engine.request_reset()
     kind = self._action_space.compile()['kind']
     shape, dtype = ((self.n_envs, 2), torch.int32) if kind == 'embodied' else (
@@ -411,6 +505,17 @@ class BatchedEnvironment(object):
     return self._action_space
 
   def close(self):
+    if self._worker is not None:
+      if self._inflight is not None:
+        try:
+          self._inflight['future'].result()
+        except Exception:  # pragma: no cover
+          pass
+        self._inflight = None
+      self._worker.shutdown(wait=True)
+      self._worker = None
+    if self._engine.device.type == 'cuda':
+      torch.cuda.synchronize(self._engine.device)
     for r in self._rasters.values():
       r.close()
     self._engine.close()

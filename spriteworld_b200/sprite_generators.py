@@ -79,10 +79,14 @@ def _stack_scenes(parts, where, n):
 
 
 class SpriteGenerator(object):
-  """Callable returning a list of sprites; `.batch(n)` returns a SceneLayout."""
+  """Callable returning a list of sprites; `.batch(n)` returns a SceneLayout.
 
-  def __init__(self, one, many):
+  `max_sprites` is an upper bound of the sprites in one scene, or None when a count is drawn
+  by a user callable (the batched environment sizes its sprite slots from it)."""
+
+  def __init__(self, one, many, max_sprites=None):
     self._one, self._many = one, many
+    self.max_sprites = max_sprites
 
   def __call__(self):
     return self._one()
@@ -140,7 +144,11 @@ def generate_sprites(factor_dist, num_sprites=1):
     ref_row = np.where(np.arange(width)[None, :] < count[:, None], ref_row, 0)
     return SceneLayout([SpriteTable(cols, total)], count, np.zeros_like(ref_row), ref_row)
 
-  return SpriteGenerator(one, many)
+  return SpriteGenerator(one, many, None if callable(num_sprites) else int(num_sprites))
+
+
+def _bounds(generators):
+  return [getattr(g, 'max_sprites', None) for g in generators]
 
 
 def chain_generators(*sprite_generators):
@@ -158,7 +166,8 @@ def chain_generators(*sprite_generators):
       layout = _ragged_concat(layout, batch_of(g, n, rng))
     return layout
 
-  return SpriteGenerator(one, many)
+  bounds = _bounds(sprite_generators)
+  return SpriteGenerator(one, many, None if None in bounds else sum(bounds))
 
 
 def sample_generator(sprite_generators, p=None):
@@ -177,7 +186,8 @@ def sample_generator(sprite_generators, p=None):
         where.append(rows)
     return _stack_scenes(parts, where, n)
 
-  return SpriteGenerator(one, many)
+  bounds = _bounds(sprite_generators)
+  return SpriteGenerator(one, many, None if None in bounds else max(bounds))
 
 
 def shuffle(sprite_generator):
@@ -198,4 +208,4 @@ def shuffle(sprite_generator):
     return SceneLayout(layout.tables, layout.count, layout.ref_table[rows, order],
                        layout.ref_row[rows, order])
 
-  return SpriteGenerator(one, many)
+  return SpriteGenerator(one, many, getattr(sprite_generator, 'max_sprites', None))

@@ -78,6 +78,12 @@ class Workload(object):
     a = 2 if self.action['kind'] == 'embodied' else 16
     return h * w * 3 + self.n_slots * 40 + self.n_slots * 8 + a + 8 + 2
 
+  def plugin_config(self):
+    """The workload as the reference's config dict (task, action_space, renderers,
+    init_sprites, max_episode_length) built from this package's plugin classes, i.e. what a
+    user of the reference would write; drives BatchedEnvironment in bench.py's `api` number."""
+    raise NotImplementedError('%s has no plugin-API form yet' % self.name)
+
 
 class GoalFinding(Workload):
   """C2: goal_finding SelectMove, 4096 envs x 5 sprites, 64x64
@@ -88,6 +94,22 @@ class GoalFinding(Workload):
   nodes = [dict(kind='find_goal', filter_slot=0, goal=(0.5, 0.5), weights=(1, 1),
                 terminate_distance=0.075, terminate_bonus=0.0, raw_reward_multiplier=50,
                 sparse_reward=False)]
+
+  def plugin_config(self):
+    from spriteworld_b200 import factor_distributions as distribs
+    from spriteworld_b200 import sprite_generators as gen
+    from spriteworld_b200 import tasks
+    from spriteworld_b200.configs.cobra import common
+    shared = distribs.Product(common.body_factors())
+    target_hue = distribs.Continuous('c0', 0., 0.4)
+    distractor_hue = distribs.Continuous('c0', 0.5, 0.9)
+    sprite_gen = gen.shuffle(gen.chain_generators(
+        gen.generate_sprites(distribs.Product([target_hue, shared]), num_sprites=2),
+        gen.generate_sprites(distribs.Product([distractor_hue, shared]), num_sprites=3)))
+    task = tasks.FindGoalPosition(filter_distrib=target_hue, terminate_distance=0.075)
+    cfg = common.config(task, sprite_gen, self.max_episode_length, __file__, None)
+    cfg.pop('metadata')
+    return cfg
 
   def sample_scenes(self, rng, n):
     s = self.n_slots

@@ -88,6 +88,8 @@ class OracleEngine(object):
     self._status = torch.from_numpy(bo.err)
     self._lib, self._h, self._out = _Lib(), self, None
     self._launches = 0
+    self._serial = np.zeros(self.n_envs, np.int64)       # scenes started (engine: scene_serial)
+    self._last_cursor = bo.cursor.astype(np.int64).copy()
 
   def _stream(self):
     return None
@@ -108,6 +110,7 @@ class OracleEngine(object):
     bo = self._bo
     if cursor is not None:
       bo.cursor[:] = np.asarray(cursor, np.int32)
+      self._last_cursor = bo.cursor.astype(np.int64).copy()
     # static factors of the live scene follow the cursor; positions are the live ones
     live_x, live_y = bo.cur['x'].copy(), bo.cur['y'].copy()
     bo.cur[:] = bo.pool[np.arange(self.n_envs), bo.cursor]
@@ -128,6 +131,9 @@ class OracleEngine(object):
     a = np.ascontiguousarray(actions.numpy())
     self._bo.step(a)   # KeyError for a bad Embodied direction, like the reference
     self._launches += 1
+    cur = self._bo.cursor.astype(np.int64)
+    self._serial += (cur != self._last_cursor)          # at most one scene per step
+    self._last_cursor = cur
     if raster is not None:
       frames = self.render(raster, frames)
     return engine_lib.StepResult(self._reward, self._step_type, self._success, self._status, frames)
@@ -145,6 +151,9 @@ class OracleEngine(object):
     bo = self._bo
     return dict(pos_x=bo.cur['x'].copy(), pos_y=bo.cur['y'].copy(), cursor=bo.cursor.copy(),
                 step_count=bo.step_count.copy(), reset_next=bo.reset_next.copy())
+
+  def download_state_serial(self):
+    return self._serial.copy()
 
   def state_tensors(self):
     bo = self._bo
