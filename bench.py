@@ -427,14 +427,16 @@ def api_rate(wl, E, local_rank, steps):
   max_episode_length steps, C2's worst case)."""
   import torch
   from spriteworld_b200 import environment
+  workers = max(1, min(8, usable_cores() - 2))
   env = environment.BatchedEnvironment(n_envs=E, device=local_rank, rng=np.random.RandomState(4242),
+                                       pool_depth=64, refill_threads=workers, refill_procs=workers,
                                        **wl.plugin_config())
   acts = torch.from_numpy(wl.sample_actions(np.random.RandomState(5), 16, E)).to(env.engine.device)
-  for i in range(2 * wl.max_episode_length + 3):
+  for i in range(4 * wl.max_episode_length + 3):
     env.step(acts[i % 16])
   torch.cuda.synchronize()
   ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-  n = max(steps, 5 * wl.max_episode_length)
+  n = max(steps, 20 * wl.max_episode_length)
   t0 = time.perf_counter()
   ev0.record()
   for i in range(n):
@@ -446,8 +448,11 @@ def api_rate(wl, E, local_rank, steps):
   stats = env.refill_stats()
   env.close()
   return dict(value=E * n / (ms * 1e-3), unit=UNIT, steps=n, ms_per_step=ms / n,
-              path='BatchedEnvironment.step (device actions -> StepResult on the device), scene '
-                   'ring refilled by a host worker thread over a side stream', refill=stats)
+              path='BatchedEnvironment.step (device actions -> BatchedTimeStep on the device); every '
+                   'env resets each max_episode_length steps; the scene ring (64 deep) is refilled '
+                   'asynchronously: scenes drawn through the plugin API (factor_distributions / '
+                   'sprite_generators) by %d worker processes, uploaded over a side stream' % workers,
+              host_scenes_per_sec=stats['scenes'] / max(stats['host_seconds'], 1e-9), refill=stats)
 
 
 def main():

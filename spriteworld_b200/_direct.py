@@ -147,5 +147,5 @@ def render(renderer, sprites):
                                renderer.bg_color)
     _rasters[key] = raster
   frames = eng.render(raster)
-  torch.cuda.synchronize(eng.device)
+  eng.check_render()
   return frames[0].cpu().numpy()

@@ -112,6 +112,7 @@ def load():
   L.swb_peer_copy.argtypes = [vp, vp, ctypes.c_uint64, vp]
   L.swb_state_pointers.argtypes = [vp] + [ctypes.POINTER(vp)] * 5
   L.swb_scene_serial_pointer.argtypes = [vp, ctypes.POINTER(vp)]
+  L.swb_render_status_pointer.argtypes = [vp, ctypes.POINTER(vp)]
   L.swb_download_state.argtypes = [vp, vp, vp, vp, vp, vp, vp]
   L.swb_upload_state.argtypes = [vp, vp, vp, vp, vp, vp, vp]
   L.swb_launch_count.argtypes = [vp]
@@ -130,7 +131,7 @@ EXPORTS = (
     'swb_engine_create', 'swb_engine_destroy', 'swb_upload_scenes', 'swb_request_reset',
     'swb_step', 'swb_eval_task', 'swb_apply_action', 'swb_raster_create', 'swb_raster_destroy', 'swb_render', 'swb_step_render',
     'swb_step_render_gather', 'swb_ipc_alloc', 'swb_ipc_free', 'swb_ipc_open', 'swb_ipc_close', 'swb_peer_copy',
-    'swb_step_host', 'swb_state_pointers', 'swb_scene_serial_pointer', 'swb_download_state', 'swb_upload_state',
+    'swb_step_host', 'swb_state_pointers', 'swb_scene_serial_pointer', 'swb_render_status_pointer', 'swb_download_state', 'swb_upload_state',
     'swb_launch_count')
 
 

@@ -606,6 +606,9 @@ int swb_step_host(swb_engine *eng, swb_raster *r, const void *actions, int32_t a
       cudaFree(eng->h_frames);
       eng->h_frames_bytes = 0;
       CUDA_TRY(cudaMalloc(&eng->h_frames, fbytes));
+      // written only by the render kernel's bulk copies, which initcheck does not track: zero
+      // it once so that the tool sees every byte the D2H copies read as initialised
+      CUDA_TRY(cudaMemsetAsync(eng->h_frames, 0, fbytes, stream));
       eng->h_frames_bytes = fbytes;
     }
     if (swb_step(eng, eng->h_actions, action_dtype, &eng->h_out, stream)) return 1;
@@ -651,6 +654,12 @@ int swb_state_pointers(swb_engine *eng, double **pos_x, double **pos_y, int32_t 
   if (cursor) *cursor = eng->st.cursor;
   if (step_count) *step_count = eng->st.step_count;
   if (reset_next) *reset_next = eng->st.reset_next;
+  return 0;
+}
+
+int swb_render_status_pointer(swb_engine *eng, uint8_t **render_status) {
+  if (!eng || !render_status) return fail("swb_render_status_pointer: null argument");
+  *render_status = eng->st.render_status;
   return 0;
 }
 

@@ -35,6 +35,20 @@ class StepResult(object):
     self.status, self.frames = status, frames
 
 
+OUT_BYTES_PER_ENV = 8 + 1 + 1 + 1
+
+
+def split_outputs(buf, n_envs):
+  """Views (reward f64, step_type i8, success u8, status u8) of a packed output buffer of
+  n_envs * OUT_BYTES_PER_ENV bytes (layout: all rewards, then all step types, ...)."""
+  E = int(n_envs)
+  reward = buf[:8 * E].view(torch.float64)
+  step_type = buf[8 * E:9 * E].view(torch.int8)
+  success = buf[9 * E:10 * E]
+  status = buf[10 * E:11 * E]
+  return reward, step_type, success, status
+
+
 class SerialSnapshot(object):
   """scene_serial of every env as of the steps enqueued when it was requested; `wait()` blocks
   the calling host thread (not the step stream) until the copy has landed."""
@@ -106,10 +120,10 @@ class Engine(object):
     _native.check(self._lib.swb_engine_create(ctypes.byref(cfg), ctypes.byref(h)))
     self._h = h
     E = self.n_envs
-    self._reward = torch.zeros(E, dtype=torch.float64, device=self.device)
-    self._step_type = torch.zeros(E, dtype=torch.int8, device=self.device)
-    self._success = torch.zeros(E, dtype=torch.uint8, device=self.device)
-    self._status = torch.zeros(E, dtype=torch.uint8, device=self.device)
+    # the four per-env outputs of a step are slices of ONE buffer (11 bytes per env: reward f64,
+    # step_type i8, success u8, status u8), so that a multi-GPU gather moves them in one piece
+    self.out_bytes = torch.zeros(E * OUT_BYTES_PER_ENV, dtype=torch.uint8, device=self.device)
+    self._reward, self._step_type, self._success, self._status = split_outputs(self.out_bytes, E)
     self._out = _native.StepOut(self._reward.data_ptr(), self._step_type.data_ptr(),
                                 self._success.data_ptr(), self._status.data_ptr())
 
@@ -252,6 +266,22 @@ class Engine(object):
     _native.check(self._lib.swb_render(self._h, raster._h, ctypes.c_void_p(frames.data_ptr()),
                                        self._stream()))
     return frames
+
+  def render_status(self):
+    """Zero-copy uint8 (E,) view of the per-env status of the last render() (ENV_SPAN_OVERFLOW)."""
+    if getattr(self, '_render_status_view', None) is None:
+      p = ctypes.c_void_p()
+      _native.check(self._lib.swb_render_status_pointer(self._h, ctypes.byref(p)))
+      self._render_status_view = torch.as_tensor(_DevicePointer(p.value, (self.n_envs,), '|u1'),
+                                                 device=self.device)
+    return self._render_status_view
+
+  def check_render(self):
+    """Raises if the last render() overflowed its span tables for any env (the frame would be
+    wrong).  Synchronises."""
+    if int(self.render_status().max().item()) & _native.ENV_SPAN_OVERFLOW:
+      raise _native.NativeError(
+          'render: more visible segments / spans per canvas row than the engine was sized for')
 
   def step_host(self, actions, raster=None, want_frames=True, out=None):
     """Whole call with HOST buffers (numpy in, numpy out): H2D, step, render, D2H, sync.

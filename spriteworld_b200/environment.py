@@ -39,6 +39,22 @@ def _color_map(pil_renderers):
   return next(iter(maps.values())) if maps else None
 
 
+def _require_compilable(task, action_space):
+  """The reference's task / action-space protocol is duck-typed (any object with reward/success
+  or step/action_spec works there, on the host).  Here both run on the device, so they must be
+  this package's classes (or subclasses that keep `compile()`): say so instead of failing
+  with an AttributeError."""
+  for what, obj, need in (('task', task, ('compile', '_filters_static')),
+                          ('action_space', action_space, ('compile',))):
+    missing = [m for m in need if not hasattr(obj, m)]
+    if missing:
+      raise NotImplementedError(
+          '%s %r cannot run on the device: it has no %s(). User-defined tasks and action spaces '
+          '(the reference accepts any duck-typed object) are out of scope of the B200 engine; '
+          'compose spriteworld_b200.tasks / action_spaces classes instead.'
+          % (what, type(obj).__name__, '/'.join(missing)))
+
+
 class Environment(dm_env.Environment):
   """One Spriteworld environment (drop-in for the reference class)."""
 
@@ -52,6 +68,7 @@ class Environment(dm_env.Environment):
     self._max_episode_length = max_episode_length
     self._metadata = metadata
     self._device = device
+    _require_compilable(task, action_space)
     self._pil, self._other = _split_renderers(renderers)
     self._color_to_rgb = _color_map(self._pil)
     self._nodes, self._filters = task.compile()
@@ -126,7 +143,10 @@ class Environment(dm_env.Environment):
   def _run_step(self, action_tensor):
     eng = self._engine
     res = eng.step(action_tensor)
-    frames = {name: eng.render(r) for name, r in self._rasters.items()}
+    frames = {}
+    for name, r in self._rasters.items():
+      frames[name] = eng.render(r)
+      eng.check_render()
     torch.cuda.synchronize(eng.device)
     status = int(res.status[0].item())
     if status & _native.ENV_CLUSTER_LABELS:
@@ -197,7 +217,10 @@ class Environment(dm_env.Environment):
   def observation(self):
     """Observation of the current state (renders on the device)."""
     eng = self._engine
-    frames = {name: eng.render(r) for name, r in self._rasters.items()}
+    frames = {}
+    for name, r in self._rasters.items():
+      frames[name] = eng.render(r)
+      eng.check_render()
     torch.cuda.synchronize(eng.device)
     return self._observation({name: f[0].cpu().numpy() for name, f in frames.items()})
 
@@ -238,14 +261,19 @@ class BatchedEnvironment(object):
 
   def __init__(self, task, action_space, renderers, init_sprites, keep_in_frame=True,
                max_episode_length=1000, metadata=None, n_envs=1, n_slots=None, pool_depth=8,
-               device=0, rng=None, refill=None):
+               device=0, rng=None, refill=None, refill_threads=4, refill_procs=None):
     """Args beyond the reference's Environment:
       n_envs: environments advanced in lockstep.
       n_slots: sprite slots per env; default: the generator's own bound (`max_sprites`), or,
         when a user callable draws the sprite count, the largest count seen in a probe sample.
       pool_depth: K, scenes kept per env on the device (the ring auto-resets draw from).
-      refill: 'async' (default on CUDA: a host thread samples and uploads consumed ring slots
+      refill: 'async' (default on CUDA: host threads sample and upload consumed ring slots
         over a side stream, the step stream waits only if a ring would underflow) or 'sync'.
+      refill_threads: blocks of envs an asynchronous refill is split into (each has its own
+        RandomState drawn from `rng`, so what a block draws does not depend on timing).
+      refill_procs: worker processes that sample and pack the blocks' scenes (_sampler_pool;
+        NumPy sampling is GIL-bound, threads alone do not scale it).  Default: one per block
+        for n_envs >= 1024, none below.  0: sample in the refill threads.
     """
     self._task, self._action_space = task, action_space
     self._renderers = renderers
@@ -253,6 +281,7 @@ class BatchedEnvironment(object):
     self._metadata = metadata
     self.n_envs = int(n_envs)
     self._rng = rng if rng is not None else np.random
+    _require_compilable(task, action_space)
     self._pil, self._other = _split_renderers(renderers)
     unsupported = [n for n, r in self._other.items() if not hasattr(r, 'render_batch')]
     if unsupported:
@@ -306,15 +335,33 @@ class BatchedEnvironment(object):
     self._stats = dict(refills=0, scenes=0, host_seconds=0.0, blocked_seconds=0.0, blocked=0)
     if refill == 'async':
       import concurrent.futures
+      import threading
       self._worker = concurrent.futures.ThreadPoolExecutor(1, thread_name_prefix='swb-refill')
+      n_thr = max(1, min(int(refill_threads), E))
+      self._samplers = (concurrent.futures.ThreadPoolExecutor(n_thr, thread_name_prefix='swb-sample')
+                        if n_thr > 1 else None)
+      # one RandomState per block of envs, so that the blocks' draws do not depend on timing
+      # (never `rng` itself: the step thread draws the action noise from it)
+      self._block_rngs = [np.random.RandomState(self._rng.randint(0, 2 ** 31 - 1))
+                          for _ in range(n_thr)]
+      self._block_edges = np.linspace(0, E, len(self._block_rngs) + 1).astype(np.int64)
+      self._upload_lock = threading.Lock()
+      if refill_procs is None:
+        refill_procs = n_thr if E >= 1024 and n_thr > 1 else 0
+      self._pool = None
+      if refill_procs:
+        from spriteworld_b200 import _sampler_pool
+        self._pool = _sampler_pool.SamplerPool(min(int(refill_procs), n_thr), init_sprites, slots,
+                                               self._filters, self._color_to_rgb)
 
   # -- scenes ----------------------------------------------------------------------------
   def _sample(self, n):
     return sprite_generators.batch_of(self._init_sprites, n, self._rng)
 
-  def _upload(self, layout, env_ids, ring_slots):
-    batch = scene.arrays_from_layout(layout, self._engine.n_slots, self._filters,
-                                     self._color_to_rgb)
+  def _upload(self, layout, env_ids, ring_slots, batch=None):
+    if batch is None:
+      batch = scene.arrays_from_layout(layout, self._engine.n_slots, self._filters,
+                                       self._color_to_rgb)
     self._engine.upload_scenes(batch, env_ids, ring_slots)
     if self._other:   # static factors of the pooled scenes, for factor observations
       E, K, S = self.n_envs, self._K, self._engine.n_slots
@@ -348,22 +395,34 @@ class BatchedEnvironment(object):
     out['mask'] = static[..., 0] > 0
     return out
 
-  def _refill_from(self, serial):
-    """Samples and uploads what brings every env's ring up to serial + K - 1.  `serial`: scene
-    each env was on at the snapshot.  Returns the number of scenes uploaded."""
+  def _refill_from(self, serial, lo=0, hi=None, rng=None, lock=None, pool_worker=None):
+    """Samples and uploads what brings the rings of envs [lo, hi) up to serial + K - 1.
+    `serial`: scene each env was on at the snapshot.  Returns the number of scenes uploaded."""
     K = self._K
-    want_upto = np.asarray(serial, np.int64) + (K - 1)
-    n_new = np.maximum(want_upto - self._refilled_upto, 0)
+    hi = self.n_envs if hi is None else hi
+    upto = self._refilled_upto[lo:hi]
+    want_upto = np.asarray(serial, np.int64)[lo:hi] + (K - 1)
+    n_new = np.maximum(want_upto - upto, 0)
     total = int(n_new.sum())
     if total <= 0:
       return 0
-    env_ids = np.repeat(np.arange(self.n_envs), n_new)
+    env_ids = np.repeat(np.arange(lo, hi), n_new)
     # 1..n_new[e] for every env, concatenated
     offs = np.arange(total) - np.repeat(np.cumsum(n_new) - n_new, n_new) + 1
-    absolute = np.repeat(self._refilled_upto, n_new) + offs
-    layout = self._sample(total)
-    self._upload(layout, env_ids, absolute % K)
-    self._refilled_upto = np.maximum(self._refilled_upto, want_upto)
+    absolute = np.repeat(upto, n_new) + offs
+    rng = self._rng if rng is None else rng
+    if lock is None:
+      self._upload(sprite_generators.batch_of(self._init_sprites, total, rng), env_ids, absolute % K)
+    else:   # sample and pack outside the lock; the engine's staging slots are not thread-safe
+      if pool_worker is not None:
+        batch = self._pool.sample(pool_worker, total, rng.randint(0, 2 ** 31 - 1))
+      else:
+        layout = sprite_generators.batch_of(self._init_sprites, total, rng)
+        batch = scene.arrays_from_layout(layout, self._engine.n_slots, self._filters,
+                                         self._color_to_rgb)
+      with lock:
+        self._upload(None, env_ids, absolute % K, batch=batch)
+    self._refilled_upto[lo:hi] = np.maximum(upto, want_upto)
     return total
 
   def _refill_job(self, snapshot):
@@ -374,10 +433,22 @@ class BatchedEnvironment(object):
     t0 = time.perf_counter()
     eng = self._engine
     torch.cuda.set_device(eng.device)
-    with torch.cuda.stream(eng.side_stream()):
-      n = self._refill_from(serial)
+    side = eng.side_stream()
+
+    def block(i):
+      torch.cuda.set_device(eng.device)
+      with torch.cuda.stream(side):
+        worker = i % len(self._pool) if self._pool is not None else None
+        return self._refill_from(serial, int(self._block_edges[i]), int(self._block_edges[i + 1]),
+                                 self._block_rngs[i], self._upload_lock, worker)
+
+    if self._samplers is None:
+      n = block(0)
+    else:
+      n = sum(self._samplers.map(block, range(len(self._block_rngs))))
+    with torch.cuda.stream(side):
       done = torch.cuda.Event()
-      done.record(eng.side_stream())
+      done.record(side)
     self._stats['host_seconds'] += time.perf_counter() - t0
     self._stats['refills'] += 1
     self._stats['scenes'] += n
@@ -432,7 +503,9 @@ class BatchedEnvironment(object):
   def refill_stats(self):
     """Counters of the scene-ring refill: refills, scenes sampled, host seconds spent sampling
     and packing, and how often / how long a step had to wait for scenes."""
-    return dict(self._stats, mode=self._refill_mode, pool_depth=self._K)
+    return dict(self._stats, mode=self._refill_mode, pool_depth=self._K,
+                threads=len(getattr(self, '_block_rngs', [None])),
+                procs=len(self._pool) if getattr(self, '_pool', None) is not None else 0)
 
   # -- API ---------------------------------------------------------------------------------
   @property
@@ -479,6 +552,7 @@ class BatchedEnvironment(object):
       res = eng.step(t, self._rasters[names[0]], self._frames[names[0]])
       for name in names[1:]:
         eng.render(self._rasters[name], self._frames[name])
+        res.status.bitwise_or_(eng.render_status())   # span overflow of the extra rasters
     else:
       res = eng.step(t)
     return self._timestep(res)
@@ -514,8 +588,123 @@ class BatchedEnvironment(object):
         self._inflight = None
       self._worker.shutdown(wait=True)
       self._worker = None
+      if self._samplers is not None:
+        self._samplers.shutdown(wait=True)
+      if self._pool is not None:
+        self._pool.close()
+        self._pool = None
     if self._engine.device.type == 'cuda':
       torch.cuda.synchronize(self._engine.device)
     for r in self._rasters.values():
       r.close()
     self._engine.close()
+
+
+class ShardedBatchedEnvironment(object):
+  """`n_envs_total` environments sharded by env index over the ranks of a process group, one
+  BatchedEnvironment (one GPU) per rank; every rank's step() returns the BatchedTimeStep of
+  ALL envs, ordered by global env index.
+
+  The path's single collective is the gather of a step's outputs:
+    * the frames are stored into every rank's gathered buffer by the render kernel itself, over
+      NVLink peer memory (distributed.PeerFrames, swb_step_render_gather);
+    * reward, step type, success and status (11 bytes per env, one packed buffer per rank) ride
+      along as ONE NCCL all-gather enqueued behind the kernel, which is also the completion
+      barrier of the frame stores: it cannot finish on a rank before every rank's kernel has.
+  Requires n_envs_total % world_size == 0 (equal shards; distributed.StepGatherer pads
+  otherwise).  `actions` may be this rank's shard (E_local, ...) or the global batch.
+
+  host_barrier=True (tests with several ranks on one device, where NCCL refuses to run):
+  device synchronise + host barrier, outputs gathered through the host.
+  """
+
+  def __init__(self, n_envs_total, group=None, device=None, seed=0, frame_slots=2,
+               host_barrier=False, **config):
+    import torch.distributed as dist
+    from spriteworld_b200 import distributed
+    self.group = group
+    self.world = dist.get_world_size(group)
+    self.rank = dist.get_rank(group)
+    self.n_envs_total = int(n_envs_total)
+    if self.n_envs_total % self.world:
+      raise ValueError('n_envs_total (%d) must be a multiple of the world size (%d)'
+                       % (self.n_envs_total, self.world))
+    self.env_start, self.n_local = distributed.env_shard(self.n_envs_total, self.rank, self.world)
+    if device is None:
+      device = torch.cuda.current_device()
+    self.host_barrier = host_barrier
+    # every rank draws its own scenes: same seed, rank-specific stream
+    self.local = BatchedEnvironment(n_envs=self.n_local, device=device,
+                                    rng=np.random.RandomState((int(seed) + 7919 * self.rank) % (2 ** 31)),
+                                    **config)
+    eng = self.local.engine
+    names = list(self.local._rasters)
+    if len(names) != 1:
+      raise NotImplementedError('ShardedBatchedEnvironment gathers exactly one PILRenderer observation')
+    self._image = names[0]
+    r = self.local._rasters[self._image]
+    self._peer = distributed.PeerFrames(self.n_local, (r.height, r.width, 3), eng.device,
+                                        n_slots=max(2, int(frame_slots)), group=group,
+                                        host_barrier=host_barrier)
+    self._out_all = torch.empty(self.world * self.n_local * engine_lib.OUT_BYTES_PER_ENV,
+                                dtype=torch.uint8, device=eng.device)
+    self._t = 0
+
+  @property
+  def engine(self):
+    return self.local.engine
+
+  def _local_actions(self, actions):
+    n = actions.shape[0]
+    if n == self.n_envs_total and self.world > 1:
+      return actions[self.env_start:self.env_start + self.n_local]
+    return actions
+
+  def step(self, actions):
+    import torch.distributed as dist
+    env, eng = self.local, self.local.engine
+    env._keep_ring_fresh()
+    env._t += 1
+    t = env._to_device(self._local_actions(actions))
+    targets = self._peer.slot(self._t)
+    res = eng.step_gather(t, env._rasters[self._image], targets)
+    E, W = self.n_local, self.world
+    if self.host_barrier:
+      self._peer.barrier()
+      parts = [torch.empty_like(eng.out_bytes, device='cpu') for _ in range(W)]
+      dist.all_gather(parts, eng.out_bytes.cpu(), group=self.group)
+      self._out_all.copy_(torch.cat(parts))
+    else:
+      # the step's one collective besides the frame stores; completes only after every rank's
+      # render kernel (and with it its peer stores) has
+      dist.all_gather_into_tensor(self._out_all, eng.out_bytes, group=self.group)
+    self._t += 1
+    per_rank = self._out_all.view(W, engine_lib.OUT_BYTES_PER_ENV * E)
+    reward = per_rank[:, :8 * E].contiguous().view(torch.float64).reshape(W * E)
+    step_type = per_rank[:, 8 * E:9 * E].reshape(W * E).view(torch.int8)
+    success = per_rank[:, 9 * E:10 * E].reshape(W * E)
+    status = per_rank[:, 10 * E:11 * E].reshape(W * E)
+    discount = (step_type != _native.STEP_LAST).to(torch.float32)
+    obs = collections.OrderedDict([(self._image, res.frames)])
+    return BatchedTimeStep(step_type, reward, discount, obs, success, status)
+
+  def reset(self):
+    env = self.local
+    env._resets += 1
+    env.engine.request_reset()
+    kind = env._action_space.compile()['kind']
+    shape, dtype = ((self.n_local, 2), torch.int32) if kind == 'embodied' else (
+        (self.n_local, 4), torch.float32)
+    return self.step(torch.zeros(shape, dtype=dtype, device=env.engine.device))
+
+  def observation_spec(self):
+    return self.local.observation_spec()
+
+  def action_spec(self):
+    return self.local.action_spec()
+
+  def close(self):
+    if self.local.engine.device.type == 'cuda':
+      torch.cuda.synchronize(self.local.engine.device)
+    self._peer.close()
+    self.local.close()

@@ -134,13 +134,21 @@ def _is_f32(col):
   return np.full(len(col), col.dtype == np.float32, bool)
 
 
+_SHAPE_ID_CACHE = {}
+
+
 def _shape_ids(col):
   from spriteworld_b200 import constants
   if col.dtype != object and np.issubdtype(col.dtype, np.integer):
     return col.astype(np.uint8)
-  names, inverse = np.unique(col.astype(str), return_inverse=True)   # a handful of names
-  ids = np.array([int(constants.ShapeType[str(v)]) for v in names], np.uint8)
-  return ids[inverse.reshape(-1)]
+  # object column of names (a handful of distinct ones): one dict lookup per element
+  table = _SHAPE_ID_CACHE
+  try:
+    return np.fromiter(map(table.__getitem__, col.tolist()), np.uint8, len(col))
+  except KeyError:
+    for v in set(col.tolist()):
+      table[v] = int(constants.ShapeType[str(v)])
+    return np.fromiter(map(table.__getitem__, col.tolist()), np.uint8, len(col))
 
 
 def _table_rgb(cols, color_to_rgb):

@@ -152,6 +152,9 @@ class OracleEngine(object):
     return dict(pos_x=bo.cur['x'].copy(), pos_y=bo.cur['y'].copy(), cursor=bo.cursor.copy(),
                 step_count=bo.step_count.copy(), reset_next=bo.reset_next.copy())
 
+  def check_render(self):
+    pass
+
   def download_state_serial(self):
     return self._serial.copy()
 

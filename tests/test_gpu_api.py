@@ -293,6 +293,16 @@ def test_pil_renderer_protocol():
 def test_batched_environment_matches_oracle_with_pool_refill():
   """256 envs of the sorting config for 70 steps: the pool is refilled several times;
   every output must equal the CPU oracle stepping the same scenes."""
+  _batched_environment_vs_oracle()
+
+
+def test_batched_environment_refill_from_worker_processes():
+  """The same with the refill's scenes sampled and packed by worker processes
+  (_sampler_pool), three blocks of envs over two workers."""
+  _batched_environment_vs_oracle(refill_threads=3, refill_procs=2)
+
+
+def _batched_environment_vs_oracle(**env_kwargs):
   import torch
   from oracle import oracle
   from spriteworld_b200 import constants, environment, scene, sprite_generators
@@ -303,7 +313,7 @@ def test_batched_environment_matches_oracle_with_pool_refill():
   real_batch_of = sprite_generators.batch_of
 
   env = environment.BatchedEnvironment(n_envs=E, pool_depth=K, rng=np.random.RandomState(3),
-                                       **cfg)
+                                       **dict(cfg, **env_kwargs))
   eng = env.engine
   # mirror of the device pool for the oracle, kept in sync by wrapping upload_scenes
   S = eng.n_slots
@@ -349,6 +359,8 @@ def test_batched_environment_matches_oracle_with_pool_refill():
     assert np.array_equal(ts.observation['image'].cpu().numpy(), bo.frames), t
     assert ts.discount.dtype == torch.float32
   assert n_first > E            # auto-resets happened beyond the initial one
+  stats = env.refill_stats()
+  assert stats['refills'] >= 1 and stats['scenes'] >= n_first - E
   env.close()
 
 

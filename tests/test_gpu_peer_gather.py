@@ -1,6 +1,7 @@
 """The frame gather fused into the render kernel (swb_step_render_gather + PeerFrames).
 
-Two ranks share cuda:0 (the GPU tier of the test-suite has one device): each maps the other's
+The gathered buffer is compared with the CPU oracle's frames of every rank (not with a second
+engine).  Two ranks share cuda:0 (the GPU tier of the test-suite has one device): each maps the other's
 gathered buffer through CUDA IPC and its render kernel stores every frame into both.  NCCL
 refuses two ranks on one device, so the handle exchange and the completion barrier run on
 gloo (PeerFrames(host_barrier=True)); the kernel path is the one bench.py uses at N > 1.
@@ -27,9 +28,11 @@ def _worker(rank, world, port, mode, ret):
     torch.cuda.set_device(0)
     wl = workloads.WORKLOADS['c4']()
     K = 4
-    eng, raster, _ = workloads.build_engine(wl, E, K, device=0, seed=1000 + rank)
-    twin, twin_raster, _ = workloads.build_engine(wl, E, K, device=0, seed=1000 + rank)
-    acts = torch.from_numpy(wl.sample_actions(np.random.RandomState(7 + rank), STEPS, E)).cuda()
+    from tests import fixtures
+    eng, raster, scenes = workloads.build_engine(wl, E, K, device=0, seed=1000 + rank)
+    bo = fixtures.workload_oracle(wl, scenes, E, K)      # CPU oracle over this rank's scenes
+    acts_np = wl.sample_actions(np.random.RandomState(7 + rank), STEPS, E)
+    acts = torch.from_numpy(acts_np).cuda()
     peer = distributed.PeerFrames(E, (wl.image_size[1], wl.image_size[0], 3), 'cuda:0',
                                   n_slots=2, host_barrier=True)
     ok = True
@@ -41,13 +44,14 @@ def _worker(rank, world, port, mode, ret):
         res = eng.step(acts[t], raster, peer.own_slab(t))
         peer.push(t)
         res.frames = peer.frames[t % 2]
-      plain = twin.step(acts[t], twin_raster)                # plain path, same seed
-      mine = plain.frames
-      ok = ok and torch.equal(res.reward, plain.reward) and torch.equal(res.step_type, plain.step_type)
+      bo.step(acts_np[t])                                    # the oracle, same scenes and actions
+      mine = torch.from_numpy(bo.frames.copy())
       torch.cuda.synchronize()
-      # every rank's plain frames, exchanged on the host, are what the buffer must hold
+      ok = ok and np.array_equal(res.step_type.cpu().numpy(), bo.step_type)
+      ok = ok and np.allclose(res.reward.cpu().numpy(), bo.reward, rtol=1e-14, atol=1e-13)
+      # every rank's ORACLE frames, exchanged on the host, are what the buffer must hold
       parts = [torch.empty((E,) + tuple(mine.shape[1:]), dtype=torch.uint8) for _ in range(world)]
-      dist.all_gather(parts, mine.cpu())
+      dist.all_gather(parts, mine)
       ok = ok and torch.equal(res.frames.cpu(), torch.cat(parts))
       dist.barrier()   # nobody overwrites a slot a peer is still comparing
     ret[rank] = bool(ok)
