@@ -72,7 +72,7 @@ struct RenderTargets {
 struct RenderLayout {
   int S, rows, M, band_rows, W, aa, ncx, ncy, cap;
   int off_meta, off_edge_i, off_edge_f, off_edge_yr, off_hl, off_region;
-  int off_nseg, off_rel, off_segs, off_prefix, off_xwin, off_ywin, off_scratch, off_frame, total;
+  int off_nseg, off_segs, off_prefix, off_xwin, off_ywin, off_scratch, off_frame, total;
   int scratch_bytes, segcap;
   __host__ __device__ RenderLayout(int S_, int rows_, int M_, int band_rows_, int W_, int aa_,
                                    int ncx_, int ncy_)
@@ -89,7 +89,6 @@ struct RenderLayout {
     // visible segments kept per canvas row: n one-span sprites leave at most 2n-1 pieces
     segcap = M > 1 ? 16 : (2 * S < 4 ? 4 : (2 * S > 16 ? 16 : 2 * S));
     off_nseg = take(((rows + 3) & ~3) + 8);  // +: quads of the H pass may end past the last row
-    off_rel = take(4 * HT_ROWW * 2);       // per canvas row of the current tile: first relevant segment | count << 8
     off_segs = take(rows * segcap * 4);
     off_prefix = take(ncx * 33 * 4);
     off_xwin = take(W * 4);                // per output column: win_min | len<<16 | cls<<24
@@ -683,7 +682,7 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, const RenderTarge
   const uint32_t sm0 = render_smem_base();
   const uint32_t ht0 = sm0 + (uint32_t)L.off_scratch, sm_frame = sm0 + (uint32_t)L.off_frame;
   const uint32_t sm_prefix = sm0 + (uint32_t)L.off_prefix, sm_nseg = sm0 + (uint32_t)L.off_nseg;
-  const uint32_t sm_segs = sm0 + (uint32_t)L.off_segs, sm_rel = sm0 + (uint32_t)L.off_rel;
+  const uint32_t sm_segs = sm0 + (uint32_t)L.off_segs;
   // V pass: this thread's row of the H tile (16 (warp & 3) + lane / 4) and its byte offset
   // there (k words lane % 4 ...), fixed for the whole kernel
   const int v_n0 = 16 * (warp & 3) + (lane >> 2);
@@ -706,24 +705,13 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, const RenderTarge
       const int q1 = ((int)(int16_t)(ywl & 0xFFFFu) + (int)((ywl >> 16) & 0xFFu) - 1 - tr0) >> 2;
       for (int tx0 = rxo0; tx0 <= rxo1; tx0 += nx_blk) {
         const int nx = min(nx_blk, rxo1 - tx0 + 1);
-        // ---- which segments can this tile see?  A row's list holds the visible segments of the
-        // whole canvas row, sorted by x; the ones inside [x4lo, x4hi) (the tile's tap windows,
-        // in bytes of the prefix table) are contiguous.  One thread per canvas row of the tile
-        // finds them: first index | count << 8, so that the H pass loops over those only ----
+        // A row's list holds the visible segments of the whole canvas row, sorted by x; the ones
+        // some column of this tile can see -- inside [x4lo, x4hi), the tile's tap windows in
+        // bytes of the prefix table -- are contiguous: the H pass skips the leading ones and
+        // stops at the first one past the windows
         const uint32_t xwa = s_xwin[tx0], xwb = s_xwin[tx0 + nx - 1];
         const int x4lo = (int)(int16_t)(xwa & 0xFFFFu) << 2;
         const int x4hi = ((int)(int16_t)(xwb & 0xFFFFu) + (int)((xwb >> 16) & 0xFFu)) << 2;
-        if (tid < ((q1 - q0 + 1) << 2)) {
-          const int rel = tr0 - row_b0 + (q0 << 2) + tid;  // band-relative canvas row (the lists are zero past n_rows)
-          const int n = (int)lds_u8(sm_nseg + (uint32_t)rel);
-          uint32_t seg_addr = sm_segs + (uint32_t)(rel * SEGCAP) * 4u;
-          int k = 0;
-          while (k < n && (int)((lds_u32(seg_addr) >> 10) & 0x7FFCu) <= x4lo) { ++k; seg_addr += 4u; }
-          const int first = k;
-          while (k < n && (int)((lds_u32(seg_addr) << 2) & 0x3FFCu) < x4hi) { ++k; seg_addr += 4u; }
-          asm volatile("st.shared.u16 [%0], %1;" : : "r"(sm_rel + 2u * (uint32_t)tid), "r"((uint32_t)first | ((uint32_t)(k - first) << 8)) : "memory");
-        }
-        __syncthreads();
         // ---- H pass: a thread owns NC columns (c0, c0 + cs) of a quad of canvas rows and
         // strides over the quads, so the window start/length and tap prefix table are loop
         // invariants and a row's segment records are decoded once for its columns; the four
@@ -751,7 +739,7 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, const RenderTarge
             const bool on1 = c0 + cs < nx;
             // raw shared-window addresses, advanced by one pass of quads per iteration
             const int rel0 = tr0 - row_b0 + ((q0 + qgroup) << 2);  // first canvas row of the quad, band-relative
-            uint32_t rel_addr = sm_rel + (uint32_t)(qgroup << 3);  // four u16 per quad
+            uint32_t nseg_addr = sm_nseg + (uint32_t)rel0;
             uint32_t seg_quad = sm_segs + (uint32_t)(rel0 * SEGCAP) * 4u;
             uint32_t ht_addr = ht0 + (uint32_t)(3 * c0 * HT_ROWW + q0 + qgroup) * 4u;
             const uint32_t seg_row_step = (uint32_t)SEGCAP * 4u;
@@ -759,21 +747,28 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, const RenderTarge
             const uint32_t ht_col = (uint32_t)(3 * cs * HT_ROWW) * 4u;
             const uint32_t bgw_r = (uint32_t)bg_r * 0x01010101u, bgw_g = (uint32_t)bg_g * 0x01010101u,
                            bgw_b = (uint32_t)bg_b * 0x01010101u;
-            for (int qq = q0 + qgroup; qq <= q1; qq += qstride, rel_addr += (uint32_t)(qstride << 3),
+            for (int qq = q0 + qgroup; qq <= q1; qq += qstride, nseg_addr += (uint32_t)(qstride << 2),
                      seg_quad += seg_step, ht_addr += (uint32_t)(qstride << 2)) {
-              uint32_t rel_lo, rel_hi;  // first | count << 8 of the quad's four rows
-              asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(rel_lo), "=r"(rel_hi) : "r"(rel_addr));
+              const uint32_t nseg4 = lds_u32(nseg_addr);  // segment counts of the quad's four rows
               uint32_t wr[H_NC], wg[H_NC], wb[H_NC];
 #pragma unroll
               for (int q = 0; q < H_NC; ++q) { wr[q] = bgw_r; wg[q] = bgw_g; wb[q] = bgw_b; }
-              if ((rel_lo | rel_hi) & 0xFF00FF00u) {
+              if (nseg4) {
                 uint32_t seg_addr0 = seg_quad;
 #pragma unroll 1
                 for (int i = 0; i < 4; ++i, seg_addr0 += seg_row_step) {
-                  const uint32_t fc = (i & 2 ? rel_hi : rel_lo) >> ((i & 1) << 4);
-                  int j = (int)((fc >> 8) & 255u);
+                  int j = (int)((nseg4 >> (8 * i)) & 255u);
                   if (!j) continue;
-                  uint32_t seg_addr = seg_addr0 + ((fc & 255u) << 2);
+                  uint32_t seg_addr = seg_addr0;
+                  uint32_t w;
+                  // skip the segments left of every tap window of the tile
+                  for (;;) {
+                    w = lds_u32(seg_addr);
+                    if ((int)((w >> 10) & 0x7FFCu) > x4lo) break;
+                    seg_addr += 4u;
+                    if (--j == 0) break;
+                  }
+                  if (j == 0 || (int)((w << 2) & 0x3FFCu) >= x4hi) continue;  // the row shows this tile background only
                   int ar[H_NC], ag[H_NC], ab[H_NC];
 #pragma unroll
                   for (int q = 0; q < H_NC; ++q) {
@@ -782,9 +777,7 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, const RenderTarge
                     ab[q] = bg_b * kk[q] + (1 << 21);
                   }
 #pragma unroll 1
-                  do {
-                    const uint32_t w = lds_u32(seg_addr);
-                    seg_addr += 4u;
+                  for (;;) {
                     const int xs4 = (int)((w << 2) & 0x3FFCu), xe4 = (int)((w >> 10) & 0x7FFCu);  // 4*xs, 4*(xe+1)
                     const int4 d = lds_v4(sm0 + ((w >> 21) & 0x7F0u));  // colour - background of the segment's sprite
 #pragma unroll
@@ -794,7 +787,11 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, const RenderTarge
                       const int wt = lds_s32((uint32_t)b) - lds_s32((uint32_t)a);
                       ar[q] += d.x * wt; ag[q] += d.y * wt; ab[q] += d.z * wt;
                     }
-                  } while (--j);
+                    if (--j == 0) break;
+                    seg_addr += 4u;
+                    w = lds_u32(seg_addr);
+                    if ((int)((w << 2) & 0x3FFCu) >= x4hi) break;  // right of every tap window: so are the rest
+                  }
                   // byte i of the words <- clip8 (Pillow's uint8 intermediate)
                   const uint32_t psel = c_prmt_insert[i];
 #pragma unroll
