@@ -270,6 +270,8 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, const RenderTarge
   uint8_t *s_frame = smem + L.off_frame;
   // phase-B view of the scratch area: per-row crossing lists
   const int CAP = L.cap;
+  __shared__ int4 s_tile[2][2];  // tile descriptors, one tile ahead (phase C)
+  __shared__ int s_it[4];        // the walking warp's state (sprite, row tile, column tile)
   __shared__ int s_overflow;
   __shared__ int s_item;
   __shared__ uint8_t *s_dst[SWB_MAX_PEERS];  // kPeers: the targets, indexable at run time
@@ -671,7 +673,6 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, const RenderTarge
       }
     }
   }
-  __syncthreads();
   SWB_MARK(7);
 
   // ---- phase C: per sprite region, in tiles of <= TILE_BLOCKS blocks of eight output rows
@@ -688,40 +689,94 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, const RenderTarge
   const int v_n0 = 16 * (warp & 3) + (lane >> 2);
   const uint32_t v_aoff = (uint32_t)(v_n0 * HT_ROWW + (lane & 3)) * 4u;
   const int row_bytes = rd.W * 3;
-  for (int s = 0; s < S; ++s) {
-    const int ryo0 = s_region[s * 4 + 0], ryo1 = s_region[s * 4 + 1];
-    const int rxo0 = s_region[s * 4 + 2], rxo1 = s_region[s * 4 + 3];
-    if (ryo1 < ryo0 || rxo1 < rxo0) continue;
-    const int nb_blk = s_pny[s], nx_blk = s_pnx[s];
-    const int rb1 = ryo1 >> 3;
-    for (int tb0 = ryo0 >> 3; tb0 <= rb1; tb0 += nb_blk) {
-      const int tb1 = min(tb0 + nb_blk - 1, rb1);
-      // outputs of the region inside this tile, the canvas rows their windows span, and the
-      // tile's row origin: the 4-aligned first row of its first block
-      const int yo_first = max(ryo0, tb0 << 3), yo_last = min(ryo1, (tb1 << 3) + 7);
-      const int tr0 = (int)(int16_t)(s_ywin[(tb0 << 3) - yo_b0] & 0xFFFFu) & ~3;
-      const uint32_t ywl = s_ywin[yo_last - yo_b0];
-      const int q0 = ((int)(int16_t)(s_ywin[yo_first - yo_b0] & 0xFFFFu) - tr0) >> 2;
-      const int q1 = ((int)(int16_t)(ywl & 0xFFFFu) + (int)((ywl >> 16) & 0xFFu) - 1 - tr0) >> 2;
-      for (int tx0 = rxo0; tx0 <= rxo1; tx0 += nx_blk) {
-        const int nx = min(nx_blk, rxo1 - tx0 + 1);
-        // A row's list holds the visible segments of the whole canvas row, sorted by x; the ones
-        // some column of this tile can see -- inside [x4lo, x4hi), the tile's tap windows in
-        // bytes of the prefix table -- are contiguous: the H pass skips the leading ones and
-        // stops at the first one past the windows
-        const uint32_t xwa = s_xwin[tx0], xwb = s_xwin[tx0 + nx - 1];
-        const int x4lo = (int)(int16_t)(xwa & 0xFFFFu) << 2;
-        const int x4hi = ((int)(int16_t)(xwb & 0xFFFFu) + (int)((xwb >> 16) & 0xFFu)) << 2;
+  // The tile loop is driven by the last warp alone: it walks (sprite, row tile, column tile) and
+  // publishes each tile as a descriptor of eight words one tile ahead (during the previous
+  // tile's H pass; the barriers of the loop order it), so the other seven warps do not repeat
+  // the walk and the scalar arithmetic behind a tile.
+  //   d0 = (tx0, nx (0: no more tiles), tb0 | nblk << 8 | yo_first << 16 | yo_last << 24  [band-relative], tr0)
+  //   d1 = (q0 | q1 << 8, x4lo, x4hi, 2^20 / cs + 1)
+  // (the iterator's state lives in shared memory: registers are per thread, and only one warp walks)
+  if (tid == (NWARP - 1) * 32) { s_it[0] = -1; s_it[1] = 0; s_it[2] = 0; }
+  __syncwarp();
+  auto next_tile = [&](int slot) {   // one warp only
+    int it_s = s_it[0], it_tb0 = s_it[1], it_tx0 = s_it[2];
+    int it_ryo0 = 0, it_ryo1 = -1, it_rxo0 = 0, it_rxo1 = -1, it_nb = 1, it_nxb = 1;
+    if (it_s >= 0) {
+      it_ryo0 = s_region[it_s * 4 + 0]; it_ryo1 = s_region[it_s * 4 + 1];
+      it_rxo0 = s_region[it_s * 4 + 2]; it_rxo1 = s_region[it_s * 4 + 3];
+      it_nb = s_pny[it_s]; it_nxb = s_pnx[it_s];
+    }
+    // advance: next column tile, else next row tile, else the next sprite with a region
+    it_tx0 += it_nxb;
+    if (it_s < 0 || it_tx0 > it_rxo1) {
+      it_tb0 += it_nb;
+      it_tx0 = it_rxo0;
+      if (it_s < 0 || it_tb0 > (it_ryo1 >> 3)) {
+        for (++it_s; it_s < S; ++it_s) {
+          it_ryo0 = s_region[it_s * 4 + 0]; it_ryo1 = s_region[it_s * 4 + 1];
+          it_rxo0 = s_region[it_s * 4 + 2]; it_rxo1 = s_region[it_s * 4 + 3];
+          if (it_ryo1 >= it_ryo0 && it_rxo1 >= it_rxo0) break;
+        }
+        if (it_s >= S) {
+          if (lane == 0) s_tile[slot][0] = make_int4(0, 0, 0, 0);
+          return;
+        }
+        it_nb = s_pny[it_s]; it_nxb = s_pnx[it_s];
+        it_tb0 = it_ryo0 >> 3;
+        it_tx0 = it_rxo0;
+      }
+    }
+    const int tb0 = it_tb0, tb1 = min(tb0 + it_nb - 1, it_ryo1 >> 3);
+    const int tx0 = it_tx0, nx = min(it_nxb, it_rxo1 - tx0 + 1);
+    // outputs of the region inside this tile, the canvas rows their windows span, and the
+    // tile's row origin: the 4-aligned first row of its first block
+    const int yo_first = max(it_ryo0, tb0 << 3), yo_last = min(it_ryo1, (tb1 << 3) + 7);
+    const int tr0 = (int)(int16_t)(s_ywin[(tb0 << 3) - yo_b0] & 0xFFFFu) & ~3;
+    const uint32_t ywl = s_ywin[yo_last - yo_b0];
+    const int q0 = ((int)(int16_t)(s_ywin[yo_first - yo_b0] & 0xFFFFu) - tr0) >> 2;
+    const int q1 = ((int)(int16_t)(ywl & 0xFFFFu) + (int)((ywl >> 16) & 0xFFu) - 1 - tr0) >> 2;
+    // [x4lo, x4hi): the tile's tap windows in bytes of the prefix table (4 * canvas x)
+    const uint32_t xwa = s_xwin[tx0], xwb = s_xwin[tx0 + nx - 1];
+    const int x4lo = (int)(int16_t)(xwa & 0xFFFFu) << 2;
+    const int x4hi = ((int)(int16_t)(xwb & 0xFFFFu) + (int)((xwb >> 16) & 0xFFu)) << 2;
+    __syncwarp();  // every lane has read the state lane 0 overwrites
+    if (lane == 0) {
+      s_it[0] = it_s; s_it[1] = it_tb0; s_it[2] = it_tx0;
+      s_tile[slot][0] = make_int4(tx0, nx,
+                                  (tb0 - (yo_b0 >> 3)) | ((tb1 - tb0 + 1) << 8) | ((yo_first - yo_b0) << 16) |
+                                      ((yo_last - yo_b0) << 24),
+                                  tr0);
+      s_tile[slot][1] = make_int4(q0 | (q1 << 8), x4lo, x4hi, (int)c_inv20[(nx + H_NC - 1) / H_NC]);
+    }
+  };
+  if (warp == NWARP - 1) next_tile(0);
+  // the background (and later the tiles) is written through the generic proxy; the bulk copy of
+  // phase D reads the staged frame through the async proxy
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();  // also: the staged frame's background is in place
+  for (int tile = 0;; ++tile) {
+        const int4 d0 = s_tile[tile & 1][0], d1 = s_tile[tile & 1][1];
+        const int nx = d0.y;
+        if (nx == 0) break;
+        const int tx0 = d0.x, tr0 = d0.w;
+        const int tb0 = (yo_b0 >> 3) + (d0.z & 255), tb1 = tb0 + ((d0.z >> 8) & 255) - 1;
+        const int yo_first = yo_b0 + ((d0.z >> 16) & 255), yo_last = yo_b0 + ((d0.z >> 24) & 255);
+        const int q0 = d1.x & 255, q1 = d1.x >> 8;
+        const int x4lo = d1.y, x4hi = d1.z;
         // ---- H pass: a thread owns NC columns (c0, c0 + cs) of a quad of canvas rows and
         // strides over the quads, so the window start/length and tap prefix table are loop
         // invariants and a row's segment records are decoded once for its columns; the four
         // uint8 results of a (column, channel) leave as one word ----
         {
           const int cs = (nx + H_NC - 1) / H_NC;  // column stride = threads per quad
-          const uint32_t inv_cs = nx == nx_blk ? (uint32_t)s_pinvh[s] : c_inv20[cs];
+          const uint32_t inv_cs = (uint32_t)d1.w;
           const int qgroup = (int)(((uint32_t)tid * inv_cs) >> 20);  // tid / cs
           const int c0 = tid - qgroup * cs;
           const int qstride = (int)(((uint32_t)R_THREADS * inv_cs) >> 20);  // quads per pass
+          // (consecutive thread groups take consecutive quads on purpose: the sprite's own rows then
+          // fill whole warps; spreading them over all warps for balance at the barrier was measured
+          // 13 % slower -- every warp then runs the segment loop half empty)
+          const int qslot = qgroup;
           if (qgroup < qstride) {
             // per column: prefix-table window [plo, phi] (shared byte addresses) and the offset
             // that maps 4*x to the address of P[x - xmin]; clamping the sum to [plo, phi] is
@@ -738,16 +793,16 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, const RenderTarge
             }
             const bool on1 = c0 + cs < nx;
             // raw shared-window addresses, advanced by one pass of quads per iteration
-            const int rel0 = tr0 - row_b0 + ((q0 + qgroup) << 2);  // first canvas row of the quad, band-relative
+            const int rel0 = tr0 - row_b0 + ((q0 + qslot) << 2);  // first canvas row of the quad, band-relative
             uint32_t nseg_addr = sm_nseg + (uint32_t)rel0;
             uint32_t seg_quad = sm_segs + (uint32_t)(rel0 * SEGCAP) * 4u;
-            uint32_t ht_addr = ht0 + (uint32_t)(3 * c0 * HT_ROWW + q0 + qgroup) * 4u;
+            uint32_t ht_addr = ht0 + (uint32_t)(3 * c0 * HT_ROWW + q0 + qslot) * 4u;
             const uint32_t seg_row_step = (uint32_t)SEGCAP * 4u;
             const uint32_t seg_step = (uint32_t)(qstride * 4 * SEGCAP) * 4u;
             const uint32_t ht_col = (uint32_t)(3 * cs * HT_ROWW) * 4u;
             const uint32_t bgw_r = (uint32_t)bg_r * 0x01010101u, bgw_g = (uint32_t)bg_g * 0x01010101u,
                            bgw_b = (uint32_t)bg_b * 0x01010101u;
-            for (int qq = q0 + qgroup; qq <= q1; qq += qstride, nseg_addr += (uint32_t)(qstride << 2),
+            for (int qq = q0 + qslot; qq <= q1; qq += qstride, nseg_addr += (uint32_t)(qstride << 2),
                      seg_quad += seg_step, ht_addr += (uint32_t)(qstride << 2)) {
               const uint32_t nseg4 = lds_u32(nseg_addr);  // segment counts of the quad's four rows
               uint32_t wr[H_NC], wg[H_NC], wb[H_NC];
@@ -864,10 +919,14 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, const RenderTarge
             }
           }
         }
+        // the last warp has the least to do in the V pass (at most one block of the fourth row
+        // tile): it publishes the next tile's descriptor, visible after the barrier below
+        if (warp == NWARP - 1) next_tile((tile + 1) & 1);
+        // the tiles are written through the generic proxy; the bulk copy of phase D reads them
+        // through the async proxy
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
         SWB_MARK(9);
-      }
-    }
   }
 
   // ---- phase D: staged frame -> HBM.  The frame is staged in destination order (rows already
@@ -880,9 +939,6 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, const RenderTarge
   const int n_bytes = n_yo * row_bytes;
   const size_t band_off = (size_t)(targets.env_offset + e) * rd.H * row_bytes + (size_t)(rd.H - yo_b1) * row_bytes;
   if ((n_bytes & 15) == 0 && (band_off & 15) == 0) {
-    // the tiles were written through the generic proxy; make them visible to the async proxy
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
     if (tid == 0) {
       const uint32_t src = (uint32_t)__cvta_generic_to_shared(s_frame);
       // peers in an order rotated by rank and frame, so that at any moment the ranks' copies are
