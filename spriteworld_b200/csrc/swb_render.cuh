@@ -49,12 +49,13 @@ constexpr int R_THREADS = 256;
 #endif
 constexpr int R_CTAS_PER_SM = SWB_RENDER_CTAS;  // resident CTAs per SM the register budget is set for
 constexpr int H_NC = 2;           // output columns one H-pass thread owns
-constexpr int TILE_X_MAX = 21;    // output columns per tile: 63 (column, channel) rows of the H tile
+constexpr int TILE_X_MAX = 20;    // output columns per tile
 constexpr int TILE_BLOCKS = 3;    // blocks of eight output rows per tile
-constexpr int HT_N = 64;          // (column, channel) rows of the H tile = 4 MMA row tiles of 16
+constexpr int HT_N = 3 * TILE_X_MAX;  // (column, channel) rows of the H tile; the fourth MMA row tile of 16
+                                  // reads four rows (and a k-step's tail) past it, into the staged frame
+                                  // that follows in shared memory: values that are never stored
 constexpr int HT_ROWW = 44;       // words per row = 176 canvas rows; = 4 mod 8: fragment loads hit 32 banks
-constexpr int HT_PAD = 24;        // words the last row's k-steps may read past its end (zero taps)
-constexpr int HT_WORDS = HT_N * HT_ROWW + HT_PAD;
+constexpr int HT_WORDS = HT_N * HT_ROWW;
 constexpr int MAX_ROW_SPANS = 12;
 constexpr int EV = SWB_MAX_VERTS;  // edge slots per sprite
 static_assert(EV == 32, "phase A maps one lane to one vertex / edge");
@@ -79,15 +80,15 @@ struct RenderLayout {
       : S(S_), rows(rows_), M(M_), band_rows(band_rows_), W(W_), aa(aa_), ncx(ncx_), ncy(ncy_) {
     int o = 0;
     auto take = [&](int bytes) { int r = o; o += (bytes + 15) & ~15; return r; };
-    take(SWB_MAX_SLOTS * 16);              // offset 0: colour - background per channel (int4 per sprite)
-    off_meta = take(S * (12 + 8) * 4);     // 12 plan ints + 8 active-edge masks per sprite
+    take(S * 16);                          // offset 0: colour - background per channel (int4 per sprite)
+    off_meta = take(S * (10 + 8) * 4);     // 10 plan ints + 8 active-edge masks per sprite
     off_edge_i = take(S * EV * 2 * 4);     // x0, y0
     off_edge_f = take(S * EV * 3 * 4);     // dx, ovs (override on the first row), ove (on the last row)
     off_edge_yr = take(S * EV * 4);        // ymin | ymax<<16 of non-horizontal edges, empty otherwise
     off_hl = take(S * EV * 3 * 2);         // horizontal edges: y, xmin, xmax (int16)
     off_region = take(S * 4 * 2);
     // visible segments kept per canvas row: n one-span sprites leave at most 2n-1 pieces
-    segcap = M > 1 ? 16 : (2 * S < 4 ? 4 : (2 * S > 16 ? 16 : 2 * S));
+    segcap = M > 1 ? 16 : (2 * S - 1 < 3 ? 3 : (2 * S - 1 > 16 ? 16 : 2 * S - 1));
     off_nseg = take(((rows + 3) & ~3) + 8);  // +: quads of the H pass may end past the last row
     off_segs = take(rows * segcap * 4);
     off_prefix = take(ncx * 33 * 4);
@@ -103,6 +104,8 @@ struct RenderLayout {
     off_scratch = take(ht_bytes);
     off_frame = take(frame_bytes);
     scratch_bytes = o - off_scratch;
+    // the V pass may read up to row 63 of the H tile and 24 words past it (see HT_N)
+    if (o < off_scratch + (64 * HT_ROWW + 24) * 4) o = off_scratch + (64 * HT_ROWW + 24) * 4;
     total = o;
   }
 };
@@ -246,9 +249,9 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, const RenderTarge
   // tile plan of the region, "has a corner join"
   int *s_nv = reinterpret_cast<int *>(smem + L.off_meta);
   int *s_pymax = s_nv + S, *s_r0 = s_pymax + S, *s_rcnt = s_r0 + S, *s_nh = s_rcnt + S;
-  int *s_bsh = s_nh + S, *s_dr = s_bsh + S;
-  int *s_pny = s_dr + S, *s_pnx = s_pny + S;
-  int *s_pinvh = s_pnx + S, *s_hasov = s_pinvh + S;
+  int *s_bsh = s_nh + S;
+  int *s_pny = s_bsh + S, *s_pnx = s_pny + S;
+  int *s_hasov = s_pnx + S;
   unsigned *s_emask = reinterpret_cast<unsigned *>(s_hasov + S);  // [S][8] active edges per row bucket
   int4 *s_dcol = reinterpret_cast<int4 *>(smem);  // [SWB_MAX_SLOTS] at offset 0: its address is a constant
   // edge table: start vertex, slope, corner-join overrides on the first / last row
@@ -481,7 +484,6 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, const RenderTarge
         pnx = ntx <= 64 ? div20(rw + ntx - 1, ntx) : (rw + ntx - 1) / ntx;
       }
       s_pny[s] = pny; s_pnx[s] = pnx;
-      s_pinvh[s] = (int)c_inv20[(pnx + H_NC - 1) / H_NC];
     }
   }
   // the previous frame's write-out must have read the staged frame before phase B reuses the
