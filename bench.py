@@ -427,10 +427,8 @@ def api_rate(wl, E, local_rank, steps):
   max_episode_length steps, C2's worst case)."""
   import torch
   from spriteworld_b200 import environment
-  workers = max(1, min(8, usable_cores() - 2))
   env = environment.BatchedEnvironment(n_envs=E, device=local_rank, rng=np.random.RandomState(4242),
-                                       pool_depth=64, refill_threads=workers, refill_procs=workers,
-                                       **wl.plugin_config())
+                                       pool_depth=32, **wl.plugin_config())
   acts = torch.from_numpy(wl.sample_actions(np.random.RandomState(5), 16, E)).to(env.engine.device)
   for i in range(4 * wl.max_episode_length + 3):
     env.step(acts[i % 16])
@@ -449,9 +447,9 @@ def api_rate(wl, E, local_rank, steps):
   env.close()
   return dict(value=E * n / (ms * 1e-3), unit=UNIT, steps=n, ms_per_step=ms / n,
               path='BatchedEnvironment.step (device actions -> BatchedTimeStep on the device); every '
-                   'env resets each max_episode_length steps; the scene ring (64 deep) is refilled '
+                   'env resets each max_episode_length steps; the scene ring (32 deep) is refilled '
                    'asynchronously: scenes drawn through the plugin API (factor_distributions / '
-                   'sprite_generators) by %d worker processes, uploaded over a side stream' % workers,
+                   'sprite_generators) by one host thread, uploaded over a side stream',
               host_scenes_per_sec=stats['scenes'] / max(stats['host_seconds'], 1e-9), refill=stats)
 
 

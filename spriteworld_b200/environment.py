@@ -261,7 +261,7 @@ class BatchedEnvironment(object):
 
   def __init__(self, task, action_space, renderers, init_sprites, keep_in_frame=True,
                max_episode_length=1000, metadata=None, n_envs=1, n_slots=None, pool_depth=8,
-               device=0, rng=None, refill=None, refill_threads=4, refill_procs=None):
+               device=0, rng=None, refill=None, refill_threads=1, refill_procs=0):
     """Args beyond the reference's Environment:
       n_envs: environments advanced in lockstep.
       n_slots: sprite slots per env; default: the generator's own bound (`max_sprites`), or,
@@ -271,9 +271,11 @@ class BatchedEnvironment(object):
         over a side stream, the step stream waits only if a ring would underflow) or 'sync'.
       refill_threads: blocks of envs an asynchronous refill is split into (each has its own
         RandomState drawn from `rng`, so what a block draws does not depend on timing).
-      refill_procs: worker processes that sample and pack the blocks' scenes (_sampler_pool;
-        NumPy sampling is GIL-bound, threads alone do not scale it).  Default: one per block
-        for n_envs >= 1024, none below.  0: sample in the refill threads.
+      refill_procs: worker processes that sample and pack the blocks' scenes at the same time
+        (_sampler_pool; NumPy sampling is GIL-bound, threads do not scale it).  0 (default): the
+        refill thread samples block after block.  Opt-in: in isolation eight workers deliver
+        2 M scenes/s on the GPU box, but next to a stepping process they were measured running
+        one after the other there, slower than the in-process sampler.
     """
     self._task, self._action_space = task, action_space
     self._renderers = renderers
@@ -332,22 +334,19 @@ class BatchedEnvironment(object):
     self._period = max(1, (K - 2) // 2 if refill == 'async' else 2 * (K - 2))
     self._inflight = None          # async: dict(snapshot step/resets, future)
     self._worker = None
-    self._stats = dict(refills=0, scenes=0, host_seconds=0.0, blocked_seconds=0.0, blocked=0)
+    self._stats = dict(refills=0, scenes=0, host_seconds=0.0, blocked_seconds=0.0, blocked=0,
+                       sample_seconds=0.0, lock_wait_seconds=0.0, upload_seconds=0.0)
     if refill == 'async':
       import concurrent.futures
       import threading
       self._worker = concurrent.futures.ThreadPoolExecutor(1, thread_name_prefix='swb-refill')
       n_thr = max(1, min(int(refill_threads), E))
-      self._samplers = (concurrent.futures.ThreadPoolExecutor(n_thr, thread_name_prefix='swb-sample')
-                        if n_thr > 1 else None)
       # one RandomState per block of envs, so that the blocks' draws do not depend on timing
       # (never `rng` itself: the step thread draws the action noise from it)
       self._block_rngs = [np.random.RandomState(self._rng.randint(0, 2 ** 31 - 1))
                           for _ in range(n_thr)]
       self._block_edges = np.linspace(0, E, len(self._block_rngs) + 1).astype(np.int64)
       self._upload_lock = threading.Lock()
-      if refill_procs is None:
-        refill_procs = n_thr if E >= 1024 and n_thr > 1 else 0
       self._pool = None
       if refill_procs:
         from spriteworld_b200 import _sampler_pool
@@ -395,58 +394,73 @@ class BatchedEnvironment(object):
     out['mask'] = static[..., 0] > 0
     return out
 
-  def _refill_from(self, serial, lo=0, hi=None, rng=None, lock=None, pool_worker=None):
-    """Samples and uploads what brings the rings of envs [lo, hi) up to serial + K - 1.
-    `serial`: scene each env was on at the snapshot.  Returns the number of scenes uploaded."""
+  def _plan_block(self, serial, lo, hi):
+    """Ring slots of envs [lo, hi) to refill so that every ring reaches serial + K - 1:
+    (env ids, absolute scene indices, new `refilled_upto`) or None."""
     K = self._K
-    hi = self.n_envs if hi is None else hi
     upto = self._refilled_upto[lo:hi]
     want_upto = np.asarray(serial, np.int64)[lo:hi] + (K - 1)
     n_new = np.maximum(want_upto - upto, 0)
     total = int(n_new.sum())
     if total <= 0:
-      return 0
+      return None
     env_ids = np.repeat(np.arange(lo, hi), n_new)
     # 1..n_new[e] for every env, concatenated
     offs = np.arange(total) - np.repeat(np.cumsum(n_new) - n_new, n_new) + 1
     absolute = np.repeat(upto, n_new) + offs
-    rng = self._rng if rng is None else rng
-    if lock is None:
-      self._upload(sprite_generators.batch_of(self._init_sprites, total, rng), env_ids, absolute % K)
-    else:   # sample and pack outside the lock; the engine's staging slots are not thread-safe
-      if pool_worker is not None:
-        batch = self._pool.sample(pool_worker, total, rng.randint(0, 2 ** 31 - 1))
-      else:
-        layout = sprite_generators.batch_of(self._init_sprites, total, rng)
-        batch = scene.arrays_from_layout(layout, self._engine.n_slots, self._filters,
-                                         self._color_to_rgb)
-      with lock:
-        self._upload(None, env_ids, absolute % K, batch=batch)
-    self._refilled_upto[lo:hi] = np.maximum(upto, want_upto)
-    return total
+    return env_ids, absolute, np.maximum(upto, want_upto)
+
+  def _refill_from(self, serial, rng=None):
+    """Synchronous form: samples (in this thread, from `rng`) and uploads what brings every
+    env's ring up to serial + K - 1.  Returns the number of scenes uploaded."""
+    plan = self._plan_block(serial, 0, self.n_envs)
+    if plan is None:
+      return 0
+    env_ids, absolute, upto = plan
+    layout = sprite_generators.batch_of(self._init_sprites, len(env_ids),
+                                        self._rng if rng is None else rng)
+    self._upload(layout, env_ids, absolute % self._K)
+    self._refilled_upto[:] = upto
+    return len(env_ids)
 
   def _refill_job(self, snapshot):
-    """Worker thread: wait for the snapshot copy (not for the step stream), sample, pack,
-    upload over the side stream.  Returns the event after which the scenes are in the pool."""
+    """Worker thread: wait for the snapshot copy (not for the step stream), have the blocks'
+    scenes drawn and packed -- all worker processes at once, or here, block after block --
+    and upload them over the side stream.  Returns the event after which they are in the pool."""
     import time
     serial = snapshot.wait()
     t0 = time.perf_counter()
     eng = self._engine
     torch.cuda.set_device(eng.device)
     side = eng.side_stream()
-
-    def block(i):
-      torch.cuda.set_device(eng.device)
-      with torch.cuda.stream(side):
-        worker = i % len(self._pool) if self._pool is not None else None
-        return self._refill_from(serial, int(self._block_edges[i]), int(self._block_edges[i + 1]),
-                                 self._block_rngs[i], self._upload_lock, worker)
-
-    if self._samplers is None:
-      n = block(0)
-    else:
-      n = sum(self._samplers.map(block, range(len(self._block_rngs))))
+    K, n = self._K, 0
+    edges = self._block_edges
+    plans = [self._plan_block(serial, int(edges[i]), int(edges[i + 1])) for i in range(len(edges) - 1)]
+    self._stats['plan_seconds'] = self._stats.get('plan_seconds', 0.0) + time.perf_counter() - t0
     with torch.cuda.stream(side):
+      if self._pool is not None:
+        # every worker draws its block at the same time; collect and upload in block order
+        for i, plan in enumerate(plans):
+          if plan is not None:
+            self._pool.request(i % len(self._pool), len(plan[0]), self._block_rngs[i].randint(0, 2 ** 31 - 1))
+            if (i + 1) % len(self._pool) == 0 or i + 1 == len(plans):
+              for j in range(i - i % len(self._pool), i + 1):
+                if plans[j] is not None:
+                  tc = time.perf_counter()
+                  batch = self._pool.collect(j % len(self._pool))
+                  t1 = time.perf_counter()
+                  self._stats['sample_seconds'] += t1 - tc   # waiting for / receiving the worker's block
+                  self._upload(None, plans[j][0], plans[j][1] % K, batch=batch)
+                  self._stats['upload_seconds'] += time.perf_counter() - t1
+      else:
+        for i, plan in enumerate(plans):
+          if plan is not None:
+            layout = sprite_generators.batch_of(self._init_sprites, len(plan[0]), self._block_rngs[i])
+            self._upload(layout, plan[0], plan[1] % K)
+      for i, plan in enumerate(plans):
+        if plan is not None:
+          self._refilled_upto[int(edges[i]):int(edges[i + 1])] = plan[2]
+          n += len(plan[0])
       done = torch.cuda.Event()
       done.record(side)
     self._stats['host_seconds'] += time.perf_counter() - t0
@@ -588,8 +602,6 @@ class BatchedEnvironment(object):
         self._inflight = None
       self._worker.shutdown(wait=True)
       self._worker = None
-      if self._samplers is not None:
-        self._samplers.shutdown(wait=True)
       if self._pool is not None:
         self._pool.close()
         self._pool = None
