@@ -180,44 +180,80 @@ def arrays_from_layout(layout, n_slots, filters=(), color_to_rgb=None):
   if layout.n and int(layout.count.max()) > n_slots:
     raise ValueError('a scene has %d sprites but the engine has %d slots'
                      % (int(layout.count.max()), n_slots))
-  per_table = []
-  for table in layout.tables:
-    if table.rows == 0:
-      per_table.append(None)
-      continue
-    cols = _full_columns(table)
-    member = np.zeros(table.rows, np.uint32)
-    for bit, f in enumerate(filters):
-      member |= np.asarray(f.contains_batch(cols), bool).astype(np.uint32) << np.uint32(bit)
-    if '_transform' in table.columns:
-      m = table.columns['_transform']
-    else:
-      m = transform_matrices(_numeric(cols['scale']), _numeric(cols['angle']))
-    pos_f32 = table.columns.get('_pos_f32')
-    if pos_f32 is None:
-      pos_f32 = _is_f32(cols['x']) & _is_f32(cols['y'])
-    per_table.append(dict(
-        x=_numeric(cols['x']), y=_numeric(cols['y']), m=m, vx=_numeric(cols['x_vel']),
-        vy=_numeric(cols['y_vel']), member=member, shape=_shape_ids(cols['shape']),
-        pos_f32=pos_f32.astype(np.uint8), rgb=_table_rgb(cols, color_to_rgb),
-        factors=np.stack([_numeric(cols[k]) for k in ('scale', 'angle', 'c0', 'c1', 'c2')],
-                         -1).astype(np.float32)))
+  tables, offsets = _merged_tables(layout.tables)
+  per_table = [None if t.rows == 0 else _table_arrays(t, filters, color_to_rgb) for t in tables]
   n = layout.n
   b = empty_batch(n, n_slots)
   valid = layout.valid()
-  scene_i, slot_j = np.nonzero(valid)
-  dst = n_slots - layout.count[scene_i] + slot_j
-  tab, row = layout.ref_table[valid], layout.ref_row[valid]
+  if valid.all() and layout.width == n_slots:      # every slot of every scene is taken
+    flat_dst = None
+    tab, row = layout.ref_table.reshape(-1), layout.ref_row.reshape(-1)
+  else:
+    scene_i, slot_j = np.nonzero(valid)
+    flat_dst = scene_i * n_slots + (n_slots - layout.count[scene_i] + slot_j)
+    tab, row = layout.ref_table[valid], layout.ref_row[valid]
+  if offsets is not None:
+    row = row + offsets[tab]                        # the tables were concatenated into one
+    tab = None
+  fields = ('x', 'y', 'm00', 'm01', 'm10', 'm11', 'vx', 'vy', 'member', 'shape', 'pos_f32', 'rgb', 'factors')
   for t, data in enumerate(per_table):
     if data is None:
       continue
-    sel = tab == t
-    si, di, ri = scene_i[sel], dst[sel], row[sel]
-    b['x'][si, di], b['y'][si, di] = data['x'][ri], data['y'][ri]
-    for k, f in enumerate(('m00', 'm01', 'm10', 'm11')):
-      b[f][si, di] = data['m'][ri, k]
-    b['vx'][si, di], b['vy'][si, di] = data['vx'][ri], data['vy'][ri]
-    b['member'][si, di], b['shape'][si, di] = data['member'][ri], data['shape'][ri]
-    b['pos_f32'][si, di], b['rgb'][si, di] = data['pos_f32'][ri], data['rgb'][ri]
-    b['factors'][si, di] = data['factors'][ri]
+    if tab is None:
+      dst, ri = flat_dst, row
+    else:
+      sel = tab == t
+      dst, ri = (np.flatnonzero(sel) if flat_dst is None else flat_dst[sel]), row[sel]
+    for f in fields:
+      out = b[f].reshape((n * n_slots,) + b[f].shape[2:])
+      if dst is None:
+        out[...] = data[f][ri]
+      else:
+        out[dst] = data[f][ri]
   return b
+
+
+def _merged_tables(tables):
+  """Concatenates the layout's sprite tables into one when their columns have the same names
+  and dtypes (the usual case: several generate_sprites over the same factor names), so that
+  the per-table work (filters, transforms, colour map) runs once.  Returns (tables, row offset
+  of each original table or None)."""
+  live = [t for t in tables if t.rows]
+  if len(live) < 2:
+    return tables, None
+  keys = set(live[0].columns)
+  if any(set(t.columns) != keys for t in live[1:]):
+    return tables, None
+  for k in keys:
+    if len({t.columns[k].dtype for t in live}) != 1:
+      return tables, None
+  from spriteworld_b200 import sprite_generators
+  offsets = np.zeros(len(tables), np.int64)
+  run = 0
+  for i, t in enumerate(tables):
+    offsets[i] = run
+    run += t.rows
+  merged = sprite_generators.SpriteTable(
+      {k: np.concatenate([t.columns[k] for t in live]) for k in keys}, run)
+  return [merged], offsets
+
+
+def _table_arrays(table, filters, color_to_rgb):
+  cols = _full_columns(table)
+  member = np.zeros(table.rows, np.uint32)
+  for bit, f in enumerate(filters):
+    member |= np.asarray(f.contains_batch(cols), bool).astype(np.uint32) << np.uint32(bit)
+  if '_transform' in table.columns:
+    m = table.columns['_transform']
+  else:
+    m = transform_matrices(_numeric(cols['scale']), _numeric(cols['angle']))
+  pos_f32 = table.columns.get('_pos_f32')
+  if pos_f32 is None:
+    pos_f32 = _is_f32(cols['x']) & _is_f32(cols['y'])
+  return dict(
+      x=_numeric(cols['x']), y=_numeric(cols['y']), m00=m[:, 0], m01=m[:, 1], m10=m[:, 2],
+      m11=m[:, 3], vx=_numeric(cols['x_vel']), vy=_numeric(cols['y_vel']), member=member,
+      shape=_shape_ids(cols['shape']), pos_f32=pos_f32.astype(np.uint8),
+      rgb=_table_rgb(cols, color_to_rgb),
+      factors=np.stack([_numeric(cols[k]) for k in ('scale', 'angle', 'c0', 'c1', 'c2')],
+                       -1).astype(np.float32))
