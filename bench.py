@@ -490,6 +490,17 @@ def main():
     dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
   torch.cuda.set_device(local_rank)
 
+  # the plugin-API rate first, in a process that holds nothing else yet: its bound is the host
+  # sampler (NumPy), which ran three times slower after the other measurements of this process
+  # (pinned buffers, several hundred MB of frame rings) than alone
+  api = None
+  if world == 1 and not args.no_api:
+    try:
+      api = api_rate(wl, args.envs or wl.n_envs, local_rank, args.steps)
+    except Exception as ex:   # reported, never silently dropped
+      api = dict(error='%s: %s' % (type(ex).__name__, ex))
+    torch.cuda.empty_cache()
+
   sampler = ClockSampler(local_rank) if rank == 0 else None
   b = Bench(wl, args, world, rank, local_rank, args.steps, args.warmup, E=args.envs or None)
   res = b.run(args.min_seconds, sampler)
@@ -549,13 +560,6 @@ def main():
       entry['note'] = 'per-GPU shard of the 8-GPU config (envs_per_gpu of the full batch / 8)'
     configs[key] = entry
     b2.close()
-
-  api = None
-  if world == 1 and not args.no_api:
-    try:
-      api = api_rate(wl, headline_E, local_rank, args.steps)
-    except Exception as ex:   # reported, never silently dropped
-      api = dict(error='%s: %s' % (type(ex).__name__, ex))
 
   if rank != 0:
     if world > 1:

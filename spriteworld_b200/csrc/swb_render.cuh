@@ -870,6 +870,10 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, const RenderTarge
             }
           }
         }
+        // The last warp's quads are the tile's last canvas rows, usually background below the
+        // sprite: it is done early and publishes the next tile's descriptor while the warps on the
+        // sprite's rows are still in their segment loops (read after two more barriers).
+        if (warp == NWARP - 1) next_tile((tile + 1) & 1);
         __syncthreads();
         SWB_MARK(8);
         // ---- V pass on the tensor pipe: a warp takes 16 (column, channel) rows of the H tile x
@@ -921,9 +925,6 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, const RenderTarge
             }
           }
         }
-        // the last warp has the least to do in the V pass (at most one block of the fourth row
-        // tile): it publishes the next tile's descriptor, visible after the barrier below
-        if (warp == NWARP - 1) next_tile((tile + 1) & 1);
         // the tiles are written through the generic proxy; the bulk copy of phase D reads them
         // through the async proxy
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -190,3 +190,45 @@ def test_product_has_no_cpu_fallback():
       if f.endswith('.py'):
         src = open(os.path.join(dirpath, f)).read()
         assert 'import oracle' not in src and 'from oracle' not in src, f
+
+
+def test_generator_sprite_bounds():
+  """SpriteGenerator.max_sprites: exact for fixed counts, None when a user callable draws
+  the count (the batched environment sizes its sprite slots from it)."""
+  import numpy as np
+  from spriteworld_b200 import factor_distributions as distribs
+  from spriteworld_b200 import sprite_generators as gen
+  f = distribs.Product([distribs.Continuous('x', 0., 1.), distribs.Continuous('y', 0., 1.)])
+  two, three = gen.generate_sprites(f, 2), gen.generate_sprites(f, num_sprites=3)
+  drawn = gen.generate_sprites(f, num_sprites=lambda: np.random.randint(1, 4))
+  assert (two.max_sprites, three.max_sprites, drawn.max_sprites) == (2, 3, None)
+  assert gen.chain_generators(two, three).max_sprites == 5
+  assert gen.sample_generator([two, three]).max_sprites == 3
+  assert gen.shuffle(gen.chain_generators(two, three)).max_sprites == 5
+  assert gen.chain_generators(two, drawn).max_sprites is None
+  assert gen.shuffle(drawn).max_sprites is None
+
+
+def test_sampler_pool_draws_what_the_in_process_sampler_draws():
+  """_sampler_pool workers (spawned processes, results through shared memory) return exactly
+  the arrays scene.arrays_from_layout gives in this process for the same seed, also for a
+  request larger than the shared block (pickled through the pipe)."""
+  import numpy as np
+  from spriteworld_b200 import _sampler_pool, scene, sprite_generators
+  from spriteworld_b200.configs.cobra import sorting
+  cfg = sorting.get_config('train')
+  _, filters = cfg['task'].compile()
+  color_to_rgb = cfg['renderers']['image'].color_to_rgb
+  S = cfg['init_sprites'].max_sprites
+  pool = _sampler_pool.SamplerPool(2, cfg['init_sprites'], S, filters, color_to_rgb, capacity=64)
+  try:
+    for worker, n, seed in ((0, 40, 11), (1, 64, 12), (1, 100, 13)):
+      got = {k: np.array(v) for k, v in pool.sample(worker, n, seed).items()}
+      np.random.seed(seed ^ 0x5BD1E995)
+      layout = sprite_generators.batch_of(cfg['init_sprites'], n, np.random.RandomState(seed))
+      want = scene.arrays_from_layout(layout, S, filters, color_to_rgb)
+      assert sorted(got) == sorted(want)
+      for k in want:
+        assert got[k].dtype == want[k].dtype and np.array_equal(got[k], want[k]), (k, n)
+  finally:
+    pool.close()
