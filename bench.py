@@ -233,6 +233,9 @@ class Bench(object):
       self.n_gslots = max(2, int(np.ceil(160e6 / (world * self.frame_bytes))) + 1)
       try:
         self.peer = distributed.PeerFrames(E, (self.H, self.W, 3), self.dev, n_slots=self.n_gslots)
+        # reward / step type / success / status of every rank (11 bytes per env), per gathered slot
+        self.out_all = [torch.empty(world * E * 11, dtype=torch.uint8, device=self.dev)
+                        for _ in range(self.n_gslots)]
       except _native.NativeError as ex:   # raised on every rank or on none
         if rank == 0:
           sys.stderr.write('peer-memory gather unavailable (%s); using the NCCL all-gather\n' % ex)
@@ -273,8 +276,11 @@ class Bench(object):
         eng.step(self.actions[t % T], raster, peer.own_slab(dst))
         self.inflight.append((peer.push(dst), -1, dst))
       else:
+        # the per-env records ride along as ONE all-gather behind the kernel; it is also
+        # the completion barrier of the frame stores: it cannot finish before every rank's kernel has
         eng.step_gather(self.actions[t % T], raster, peer.slot(dst))
-        self.inflight.append((peer.barrier(async_op=True), -1, dst))
+        self.inflight.append((dist.all_gather_into_tensor(self.out_all[dst], eng.out_bytes, async_op=True),
+                              -1, dst))
       return
     self.wait_for(lambda it: it[1] == slot)    # the gather that last read this ring buffer
     fr = self.ring[slot]
@@ -508,7 +514,8 @@ def main():
   e2e = None if args.no_e2e else b.e2e()
   collective = ('none' if world == 1 else
                 'frames stored into every rank\'s gathered buffer by the render kernel '
-                '(NVLink peer memory) + one-element NCCL all-reduce as completion barrier'
+                '(NVLink peer memory) + one NCCL all-gather of the 11-byte per-env records (reward, step type, '
+                'success, status), which is also the completion barrier'
                 if b.peer is not None and b.gather == 'peer' else
                 'render into the rank\'s block of the gathered buffer, copy-engine pushes to '
                 'the peers over NVLink + one-element NCCL all-reduce as completion barrier'
