@@ -459,9 +459,14 @@ void swb_raster_destroy(swb_raster *r) {
   delete r;
 }
 
+// after_step: the launch follows this step's step_kernel on the stream.  It is then made a
+// programmatic dependent launch: the render CTAs may become resident and load their tables while
+// the step kernel's last CTAs run (step_kernel signals griddepcontrol.launch_dependents at once),
+// and wait (griddepcontrol.wait, after their set-up) until the step grid has completed and its
+// writes are visible.
 static int launch_render_targets(swb_engine *eng, swb_raster *r, const RenderTargets &targets,
                                  uint8_t *status, cudaStream_t stream, int env_base = 0,
-                                 int env_count = -1) {
+                                 int env_count = -1, bool after_step = false) {
   if (r->eng != eng) return fail("raster belongs to another engine");
   RasterDev rd = r->rd;
   rd.max_spans = eng->max_spans;
@@ -485,8 +490,17 @@ static int launch_render_targets(swb_engine *eng, swb_raster *r, const RenderTar
   // (env, band) items from the engine's counter; see render_kernel
   const int n_items = env_count * rd.n_bands;
   const int grid = std::min(n_items, eng->n_sms * R_CTAS_PER_SM);
-  kernel<<<grid, R_THREADS, L.total, stream>>>(st, rd, L, targets, env_base, n_items, eng->d_work,
-                                               eng->work_base);
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3(grid);
+  lc.blockDim = dim3(R_THREADS);
+  lc.dynamicSmemBytes = (size_t)L.total;
+  lc.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = attr;
+  lc.numAttrs = after_step ? 1 : 0;
+  CUDA_TRY(cudaLaunchKernelEx(&lc, kernel, st, rd, L, targets, env_base, n_items, eng->d_work, eng->work_base));
   eng->work_base += (unsigned)(n_items + grid);  // every CTA's last claim fails
   eng->launches++;
   CUDA_TRY(cudaGetLastError());
@@ -494,13 +508,14 @@ static int launch_render_targets(swb_engine *eng, swb_raster *r, const RenderTar
 }
 
 static int launch_render(swb_engine *eng, swb_raster *r, uint8_t *frames, uint8_t *status,
-                         cudaStream_t stream, int env_base = 0, int env_count = -1) {
+                         cudaStream_t stream, int env_base = 0, int env_count = -1,
+                         bool after_step = false) {
   RenderTargets targets{};
   targets.dst[0] = frames;
   targets.n = 1;
   targets.env_offset = 0;
   targets.self = 0;
-  return launch_render_targets(eng, r, targets, status, stream, env_base, env_count);
+  return launch_render_targets(eng, r, targets, status, stream, env_base, env_count, after_step);
 }
 
 int swb_render(swb_engine *eng, swb_raster *r, uint8_t *frames, void *stream_) {
@@ -515,7 +530,7 @@ int swb_step_render(swb_engine *eng, swb_raster *r, const void *actions, int32_t
                     const swb_step_out *out, uint8_t *frames, void *stream_) {
   if (!r || !frames) return fail("swb_step_render: null argument");
   if (swb_step(eng, actions, action_dtype, out, stream_)) return 1;
-  return launch_render(eng, r, frames, out->status, static_cast<cudaStream_t>(stream_));
+  return launch_render(eng, r, frames, out->status, static_cast<cudaStream_t>(stream_), 0, -1, true);
 }
 
 int swb_step_render_gather(swb_engine *eng, swb_raster *r, const void *actions,
@@ -535,7 +550,7 @@ int swb_step_render_gather(swb_engine *eng, swb_raster *r, const void *actions,
   targets.env_offset = (int)env_offset;
   targets.self = (int)((env_offset / (eng ? eng->st.E : 1)) % n_dst);
   if (swb_step(eng, actions, action_dtype, out, stream_)) return 1;
-  return launch_render_targets(eng, r, targets, out->status, static_cast<cudaStream_t>(stream_));
+  return launch_render_targets(eng, r, targets, out->status, static_cast<cudaStream_t>(stream_), 0, -1, true);
 }
 
 int swb_ipc_alloc(int32_t device, uint64_t bytes, void **ptr, uint8_t *handle) {
@@ -613,7 +628,7 @@ int swb_step_host(swb_engine *eng, swb_raster *r, const void *actions, int32_t a
     }
     if (swb_step(eng, eng->h_actions, action_dtype, &eng->h_out, stream)) return 1;
     if (!frames) {
-      if (launch_render(eng, r, eng->h_frames, eng->h_out.status, stream)) return 1;
+      if (launch_render(eng, r, eng->h_frames, eng->h_out.status, stream, 0, -1, true)) return 1;
     } else {
       // render in env chunks; each chunk's frames go to the host on a second stream while
       // the next chunk renders
@@ -626,7 +641,7 @@ int swb_step_host(swb_engine *eng, swb_raster *r, const void *actions, int32_t a
       const int n_chunks = E >= 1024 ? 8 : (E >= 64 ? 2 : 1);
       for (int c = 0; c < n_chunks; ++c) {
         const int e0 = (int)((int64_t)E * c / n_chunks), e1 = (int)((int64_t)E * (c + 1) / n_chunks);
-        if (launch_render(eng, r, eng->h_frames, eng->h_out.status, stream, e0, e1 - e0)) return 1;
+        if (launch_render(eng, r, eng->h_frames, eng->h_out.status, stream, e0, e1 - e0, c == 0)) return 1;
         CUDA_TRY(cudaEventRecord(eng->chunk_done[c], stream));
         CUDA_TRY(cudaStreamWaitEvent(eng->copy_stream, eng->chunk_done[c], 0));
         CUDA_TRY(cudaMemcpyAsync(frames + per_env * e0, eng->h_frames + per_env * e0, per_env * (e1 - e0),

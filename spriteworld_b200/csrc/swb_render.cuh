@@ -296,6 +296,10 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, const RenderTarge
   int band_loaded = -1;
   bool copy_pending = false;  // thread 0: the previous frame's bulk copy may still read s_frame
 
+  // Launched behind this step's step_kernel as a programmatic dependent launch (swb_api.cu), the
+  // CTA got here while that grid may still be running: wait until it has completed and its
+  // positions / cursors are visible.  Returns at once for an ordinary launch.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 #ifdef SWB_PHASE_CLOCKS
   long long mark_ = clock64();
 #endif

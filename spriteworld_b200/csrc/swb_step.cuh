@@ -329,6 +329,9 @@ step_kernel(DevState st, const StepCfg *__restrict__ step_cfg, const void *__res
   // the engine's own copy of the action space / episode / task tree, in global memory: a
   // kernel of engine A queued behind a launch of engine B still reads A's table
   const StepCfg &c_step = *step_cfg;
+  // the render kernel that follows on the stream may start to become resident (it waits for
+  // this grid to complete before it reads anything a step writes)
+  asm volatile("griddepcontrol.launch_dependents;");
   // mode 0: Environment.step; 1: task.reward/success of the live state only;
   // 2: action_space.step only (no velocity update, task or counters)
   __shared__ WarpSprites s_ws[STEP_WARPS];
