@@ -39,6 +39,23 @@ def _color_map(pil_renderers):
   return next(iter(maps.values())) if maps else None
 
 
+def tune_host_allocator(threshold_bytes=1 << 30):
+  """Opt-in, process-wide: keeps glibc from serving NumPy's temporaries (a few hundred KB each
+  in the scene sampler) through mmap/munmap.  Each munmap shoots down TLB entries on every CPU a
+  thread of the process has run on, and a process that drives a GPU has many threads (CUDA,
+  OpenBLAS, OpenMP pools): the sampler was measured 3.6x slower late in a process than in a
+  fresh one.  With the mmap threshold raised the arrays come from the heap instead.  Returns
+  True if mallopt accepted both settings (Linux/glibc only)."""
+  import ctypes
+  try:
+    libc = ctypes.CDLL('libc.so.6')
+    M_TRIM_THRESHOLD, M_MMAP_THRESHOLD = -1, -3
+    return bool(libc.mallopt(M_MMAP_THRESHOLD, int(threshold_bytes)) and
+                libc.mallopt(M_TRIM_THRESHOLD, int(threshold_bytes)))
+  except (OSError, AttributeError):
+    return False
+
+
 def _require_compilable(task, action_space):
   """The reference's task / action-space protocol is duck-typed (any object with reward/success
   or step/action_spec works there, on the host).  Here both run on the device, so they must be

@@ -31,7 +31,8 @@ def _hsv_arrays(h, s, v):
   g = np.choose(i, [t, v, v, q, p, p])
   b = np.choose(i, [p, p, t, v, v, q])
   grey = s == 0
-  r, g, b = np.where(grey, v, r), np.where(grey, v, g), np.where(grey, v, b)
+  if grey.any():
+    r, g, b = np.where(grey, v, r), np.where(grey, v, g), np.where(grey, v, b)
   return r, g, b
 
 
@@ -47,6 +48,15 @@ def hsv_to_rgb_batch(c0, c1, c2, is_f32):
   c0, c1, c2 = (np.asarray(a, np.float64) for a in (c0, c1, c2))
   is_f32 = np.broadcast_to(np.asarray(is_f32, bool), c0.shape)
   out = np.zeros(c0.shape + (3,), np.uint8)
+  uniform = None if is_f32.size == 0 else (True if is_f32.all() else (False if not is_f32.any() else None))
+  if uniform is not None:   # one float type for every sprite (the usual case): no masks
+    dt = np.float32 if uniform else np.float64
+    r, g, b = _hsv_arrays(c0.astype(dt), c1.astype(dt), c2.astype(dt))
+    scale = dt(255)
+    out[..., 0] = (scale * r).astype(np.uint8)
+    out[..., 1] = (scale * g).astype(np.uint8)
+    out[..., 2] = (scale * b).astype(np.uint8)
+    return out
   for f32 in (True, False):
     sel = is_f32 == f32
     if not sel.any():

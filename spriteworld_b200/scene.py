@@ -141,8 +141,24 @@ def _shape_ids(col):
   from spriteworld_b200 import constants
   if col.dtype != object and np.issubdtype(col.dtype, np.integer):
     return col.astype(np.uint8)
-  # object column of names (a handful of distinct ones): one dict lookup per element
+  # Object column of names.  Discrete.sample_batch indexes a small typed column of candidates, so
+  # the elements are a handful of distinct Python objects repeated: map each distinct POINTER once
+  # (the column's buffer is an array of PyObject*), instead of one dict lookup per element.
   table = _SHAPE_ID_CACHE
+  if len(col) >= 256 and col.flags.c_contiguous:
+    import ctypes
+    ptrs = np.ctypeslib.as_array((ctypes.c_size_t * len(col)).from_address(col.ctypes.data))
+    uniq, inverse = np.unique(ptrs, return_inverse=True)
+    if len(uniq) <= 64:
+      first = np.zeros(len(uniq), np.int64)
+      first[inverse[::-1]] = np.arange(len(col) - 1, -1, -1)   # an element index per distinct object
+      ids = np.empty(len(uniq), np.uint8)
+      for k, i in enumerate(first):
+        v = col[i]
+        if v not in table:
+          table[v] = int(constants.ShapeType[str(v)])
+        ids[k] = table[v]
+      return ids[inverse.reshape(-1)]
   try:
     return np.fromiter(map(table.__getitem__, col.tolist()), np.uint8, len(col))
   except KeyError:

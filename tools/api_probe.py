@@ -52,7 +52,9 @@ def main():
   from spriteworld_b200 import environment, workloads
   wl = workloads.WORKLOADS['c2']()
   E = wl.n_envs
-  for procs, threads, K in ((8, 8, 64), (8, 8, 128)):
+  if '--mallopt' in sys.argv:
+    print('tune_host_allocator:', environment.tune_host_allocator(), flush=True)
+  for procs, threads, K in ((0, 1, 32), (0, 1, 32)):
     env = environment.BatchedEnvironment(n_envs=E, device=0, rng=np.random.RandomState(1), pool_depth=K,
                                          refill_threads=threads, refill_procs=procs, **wl.plugin_config())
     acts = torch.from_numpy(wl.sample_actions(np.random.RandomState(5), 16, E)).to(env.engine.device)
