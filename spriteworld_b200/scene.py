@@ -40,6 +40,11 @@ def transform_matrices(scale, angle):
   angle = np.ascontiguousarray(angle, dtype=np.float64)
   if scale.size == 0:
     return np.empty(scale.shape + (4,), np.float64)
+  sb, ab = scale.reshape(-1).view(np.int64), angle.reshape(-1).view(np.int64)
+  if sb.min() == sb.max() and ab.min() == ab.max():   # one (scale, angle) bit pattern for all
+    key = (float(scale.reshape(-1)[0]), float(angle.reshape(-1)[0]))
+    m = transform_matrix(key[0], key[1])
+    return np.broadcast_to(np.array(m, np.float64), scale.shape + (4,)).copy()
   # distinct by bit pattern (0.0 and -0.0 stay apart: they give differently signed zeros);
   # two 1-D uniques and one over the combined small index are much cheaper than a row-wise one
   us, inv_s = np.unique(scale.reshape(-1).view(np.int64), return_inverse=True)
