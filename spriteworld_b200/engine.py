@@ -56,6 +56,10 @@ class SerialSnapshot(object):
   def __init__(self, host, event):
     self._host, self._event = host, event
 
+  def ready(self):
+    """True once the copy has landed (never blocks)."""
+    return self._event.query()
+
   def wait(self):
     self._event.synchronize()
     return self._host.numpy().astype(np.int64)
@@ -187,14 +191,15 @@ class Engine(object):
     """Asynchronous device->pinned copy of scene_serial, ordered after the work enqueued so far
     on the current stream and issued on the side stream.  Returns a SerialSnapshot."""
     if getattr(self, '_serial_host', None) is None:
-      self._serial_host = [torch.empty(self.n_envs, dtype=torch.int32).pin_memory() for _ in range(2)]
+      # a ring of pinned buffers: the batched environment keeps its last dozen snapshots around
+      self._serial_host = [torch.empty(self.n_envs, dtype=torch.int32).pin_memory() for _ in range(16)]
       self._serial_i = 0
     side = self.side_stream()
     ev = torch.cuda.Event()
     ev.record(torch.cuda.current_stream(self.device))
     side.wait_event(ev)
     host = self._serial_host[self._serial_i]
-    self._serial_i ^= 1
+    self._serial_i = (self._serial_i + 1) % len(self._serial_host)
     with torch.cuda.stream(side):
       host.copy_(self.scene_serial(), non_blocking=True)
       done = torch.cuda.Event()

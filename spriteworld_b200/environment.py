@@ -350,6 +350,13 @@ class BatchedEnvironment(object):
     self._safe_step, self._safe_resets = 0, 0
     self._period = max(1, (K - 2) // 2 if refill == 'async' else 2 * (K - 2))
     self._inflight = None          # async: dict(snapshot step/resets, future)
+    # async: the last snapshots of scene_serial, (step, resets, SerialSnapshot).  They are taken
+    # every few steps, ahead of need: the step stream runs tens of steps behind the host, and a
+    # refill that had to wait for a snapshot ordered behind everything enqueued would leave the
+    # sampler idle for that long; it starts from the newest snapshot that has already landed.
+    self._snaps = collections.deque(maxlen=12)
+    self._snap_every = max(1, (K - 2) // 4)
+    self._last_snap = -(1 << 30)
     self._worker = None
     self._stats = dict(refills=0, scenes=0, host_seconds=0.0, blocked_seconds=0.0, blocked=0,
                        sample_seconds=0.0, lock_wait_seconds=0.0, upload_seconds=0.0)
@@ -505,9 +512,20 @@ class BatchedEnvironment(object):
     self._safe_step, self._safe_resets = job['step'], job['resets']
     self._inflight = None
 
+  def _snapshot(self):
+    self._snaps.append((self._t, self._resets, self._engine.snapshot_scene_serial()))
+    self._last_snap = self._t
+
   def _request(self):
-    snapshot = self._engine.snapshot_scene_serial()
-    self._inflight = dict(step=self._t, resets=self._resets,
+    """Starts a refill from the newest snapshot that has landed (or, if none newer than the last
+    refill has, from the oldest pending one: it lands first)."""
+    fresh = [rec for rec in self._snaps if rec[0] > self._safe_step]
+    if not fresh:
+      self._snapshot()
+      fresh = [self._snaps[-1]]
+    landed = [rec for rec in fresh if rec[2].ready()]
+    step, resets, snapshot = landed[-1] if landed else fresh[0]
+    self._inflight = dict(step=step, resets=resets,
                           future=self._worker.submit(self._refill_job, snapshot))
 
   def _keep_ring_fresh(self):
@@ -524,6 +542,8 @@ class BatchedEnvironment(object):
         self._safe_step, self._safe_resets = self._t, self._resets
       return
     self._land(block=False)
+    if self._t - self._last_snap >= self._snap_every:
+      self._snapshot()
     if self._inflight is None and self._t - self._safe_step >= self._period:
       self._request()
     while self._risk(self._t + 1) > K - 1:   # this step could run a ring dry: wait for scenes
