@@ -63,13 +63,15 @@ def transform_matrices(scale, angle):
   return mats[inverse.reshape(-1)].reshape(scale.shape + (4,))
 
 
-def empty_batch(n_scenes, n_slots):
-  b = {f: np.zeros((n_scenes, n_slots), np.float64) for f in F64_FIELDS}
-  b['member'] = np.zeros((n_scenes, n_slots), np.uint32)
-  b['shape'] = np.zeros((n_scenes, n_slots), np.uint8)
-  b['pos_f32'] = np.zeros((n_scenes, n_slots), np.uint8)
-  b['rgb'] = np.zeros((n_scenes, n_slots, 3), np.uint8)
-  b['factors'] = np.zeros((n_scenes, n_slots, 5), np.float32)
+def empty_batch(n_scenes, n_slots, zero=True):
+  """zero=False: uninitialised arrays, for a caller that fills every slot."""
+  new = np.zeros if zero else np.empty
+  b = {f: new((n_scenes, n_slots), np.float64) for f in F64_FIELDS}
+  b['member'] = new((n_scenes, n_slots), np.uint32)
+  b['shape'] = new((n_scenes, n_slots), np.uint8)
+  b['pos_f32'] = new((n_scenes, n_slots), np.uint8)
+  b['rgb'] = new((n_scenes, n_slots, 3), np.uint8)
+  b['factors'] = new((n_scenes, n_slots, 5), np.float32)
   return b
 
 
@@ -204,8 +206,9 @@ def arrays_from_layout(layout, n_slots, filters=(), color_to_rgb=None):
   tables, offsets = _merged_tables(layout.tables)
   per_table = [None if t.rows == 0 else _table_arrays(t, filters, color_to_rgb) for t in tables]
   n = layout.n
-  b = empty_batch(n, n_slots)
   valid = layout.valid()
+  full = bool(valid.all()) and layout.width == n_slots    # every slot of every scene gets written
+  b = empty_batch(n, n_slots, zero=not full)
   if valid.all() and layout.width == n_slots:      # every slot of every scene is taken
     flat_dst = None
     tab, row = layout.ref_table.reshape(-1), layout.ref_row.reshape(-1)
@@ -227,7 +230,9 @@ def arrays_from_layout(layout, n_slots, filters=(), color_to_rgb=None):
       dst, ri = (np.flatnonzero(sel) if flat_dst is None else flat_dst[sel]), row[sel]
     for f in fields:
       out = b[f].reshape((n * n_slots,) + b[f].shape[2:])
-      if dst is None:
+      if dst is None and data[f].dtype == out.dtype:
+        np.take(data[f], ri, axis=0, out=out)     # straight into the batch, no temporary
+      elif dst is None:
         out[...] = data[f][ri]
       else:
         out[dst] = data[f][ri]
@@ -259,6 +264,13 @@ def _merged_tables(tables):
   return [merged], offsets
 
 
+def _factor_columns(cols):
+  out = np.empty((len(cols['scale']), 5), np.float32)
+  for i, k in enumerate(('scale', 'angle', 'c0', 'c1', 'c2')):
+    out[:, i] = _numeric(cols[k])     # through float64, like the stacked form it replaces
+  return out
+
+
 def _table_arrays(table, filters, color_to_rgb):
   cols = _full_columns(table)
   member = np.zeros(table.rows, np.uint32)
@@ -275,6 +287,4 @@ def _table_arrays(table, filters, color_to_rgb):
       x=_numeric(cols['x']), y=_numeric(cols['y']), m00=m[:, 0], m01=m[:, 1], m10=m[:, 2],
       m11=m[:, 3], vx=_numeric(cols['x_vel']), vy=_numeric(cols['y_vel']), member=member,
       shape=_shape_ids(cols['shape']), pos_f32=pos_f32.astype(np.uint8),
-      rgb=_table_rgb(cols, color_to_rgb),
-      factors=np.stack([_numeric(cols[k]) for k in ('scale', 'angle', 'c0', 'c1', 'c2')],
-                       -1).astype(np.float32))
+      rgb=_table_rgb(cols, color_to_rgb), factors=_factor_columns(cols))
