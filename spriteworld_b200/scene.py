@@ -174,7 +174,7 @@ def _shape_ids(col):
     return np.fromiter(map(table.__getitem__, col.tolist()), np.uint8, len(col))
 
 
-def _table_rgb(cols, color_to_rgb):
+def _table_rgb(cols, color_to_rgb, num=None):
   from spriteworld_b200.renderers import color_maps
   c = [cols['c0'], cols['c1'], cols['c2']]
   rows = len(c[0])
@@ -183,6 +183,8 @@ def _table_rgb(cols, color_to_rgb):
   homogeneous = all(a.dtype != object for a in c) and len({a.dtype for a in c}) == 1
   if color_to_rgb is color_maps.hsv_to_rgb and homogeneous and c[0].dtype in (
       np.dtype(np.float32), np.dtype(np.float64)):
+    if num is not None:
+      return color_maps.hsv_to_rgb_batch(num['c0'], num['c1'], num['c2'], c[0].dtype == np.float32)
     return color_maps.hsv_to_rgb_batch(_numeric(c[0]), _numeric(c[1]), _numeric(c[2]),
                                        c[0].dtype == np.float32)
   out = np.zeros((rows, 3), np.uint8)   # arbitrary callable or mixed scalar types
@@ -264,27 +266,41 @@ def _merged_tables(tables):
   return [merged], offsets
 
 
-def _factor_columns(cols):
-  out = np.empty((len(cols['scale']), 5), np.float32)
+def _factor_columns(num):
+  out = np.empty((len(num['scale']), 5), np.float32)
   for i, k in enumerate(('scale', 'angle', 'c0', 'c1', 'c2')):
-    out[:, i] = _numeric(cols[k])     # through float64, like the stacked form it replaces
+    out[:, i] = num[k]     # through float64, like the stacked form it replaces
   return out
+
+
+class _NumericCache(dict):
+  """cols[name] as float64, converted once per table (several consumers want the same columns)."""
+
+  def __init__(self, cols):
+    super().__init__()
+    self._cols = cols
+
+  def __missing__(self, name):
+    v = _numeric(self._cols[name])
+    self[name] = v
+    return v
 
 
 def _table_arrays(table, filters, color_to_rgb):
   cols = _full_columns(table)
+  num = _NumericCache(cols)
   member = np.zeros(table.rows, np.uint32)
   for bit, f in enumerate(filters):
     member |= np.asarray(f.contains_batch(cols), bool).astype(np.uint32) << np.uint32(bit)
   if '_transform' in table.columns:
     m = table.columns['_transform']
   else:
-    m = transform_matrices(_numeric(cols['scale']), _numeric(cols['angle']))
+    m = transform_matrices(num['scale'], num['angle'])
   pos_f32 = table.columns.get('_pos_f32')
   if pos_f32 is None:
     pos_f32 = _is_f32(cols['x']) & _is_f32(cols['y'])
   return dict(
-      x=_numeric(cols['x']), y=_numeric(cols['y']), m00=m[:, 0], m01=m[:, 1], m10=m[:, 2],
-      m11=m[:, 3], vx=_numeric(cols['x_vel']), vy=_numeric(cols['y_vel']), member=member,
+      x=num['x'], y=num['y'], m00=m[:, 0], m01=m[:, 1], m10=m[:, 2],
+      m11=m[:, 3], vx=num['x_vel'], vy=num['y_vel'], member=member,
       shape=_shape_ids(cols['shape']), pos_f32=pos_f32.astype(np.uint8),
-      rgb=_table_rgb(cols, color_to_rgb), factors=_factor_columns(cols))
+      rgb=_table_rgb(cols, color_to_rgb, num), factors=_factor_columns(num))

@@ -40,7 +40,11 @@ class SceneLayout(object):
     return self.ref_row.shape[1]
 
   def valid(self):
-    return np.arange(self.width)[None, :] < self.count[:, None]
+    v = getattr(self, '_valid', None)
+    if v is None or v.shape != self.ref_row.shape:
+      v = np.arange(self.width)[None, :] < self.count[:, None]
+      self._valid = v
+    return v
 
   def rows_of(self, index):
     """Sub-layout of the given scenes (tables are shared)."""
@@ -132,10 +136,13 @@ def generate_sprites(factor_dist, num_sprites=1):
     return [sprite_lib.Sprite(**factor_dist.sample()) for _ in range(how_many())]
 
   def many(n, rng):
-    if callable(num_sprites):
-      count = np.array([num_sprites() for _ in range(n)], np.int64)
-    else:
+    if not callable(num_sprites):   # every scene has the same count: row i*num + j, no padding
       count = np.full(n, num_sprites, np.int64)
+      total = n * int(num_sprites)
+      cols = factor_dist.sample_batch(total, rng=rng) if total else {}
+      ref_row = np.arange(total, dtype=np.int64).reshape(n, int(num_sprites))
+      return SceneLayout([SpriteTable(cols, total)], count, np.zeros_like(ref_row), ref_row)
+    count = np.array([num_sprites() for _ in range(n)], np.int64)
     total = int(count.sum())
     cols = factor_dist.sample_batch(total, rng=rng) if total else {}
     width = int(count.max()) if n else 0
