@@ -206,6 +206,18 @@ class Engine(object):
       done.record(side)
     return SerialSnapshot(host, done)
 
+  def side_stream_context(self):
+    """Context in which this thread's CUDA work (scene uploads, pool bookkeeping) goes to the
+    side stream of this engine's device."""
+    torch.cuda.set_device(self.device)
+    return torch.cuda.stream(self.side_stream())
+
+  def record_side_event(self):
+    """An event after the work enqueued so far on the side stream (for wait_event)."""
+    done = torch.cuda.Event()
+    done.record(self.side_stream())
+    return done
+
   def download_state_serial(self):
     """scene_serial as a host array, after everything enqueued so far (synchronous)."""
     return self.scene_serial().cpu().numpy().astype(np.int64)

@@ -455,13 +455,11 @@ class BatchedEnvironment(object):
     serial = snapshot.wait()
     t0 = time.perf_counter()
     eng = self._engine
-    torch.cuda.set_device(eng.device)
-    side = eng.side_stream()
     K, n = self._K, 0
     edges = self._block_edges
     plans = [self._plan_block(serial, int(edges[i]), int(edges[i + 1])) for i in range(len(edges) - 1)]
     self._stats['plan_seconds'] = self._stats.get('plan_seconds', 0.0) + time.perf_counter() - t0
-    with torch.cuda.stream(side):
+    with eng.side_stream_context():
       if self._pool is not None:
         # every worker draws its block at the same time; collect and upload in block order
         for i, plan in enumerate(plans):
@@ -485,8 +483,7 @@ class BatchedEnvironment(object):
         if plan is not None:
           self._refilled_upto[int(edges[i]):int(edges[i + 1])] = plan[2]
           n += len(plan[0])
-      done = torch.cuda.Event()
-      done.record(side)
+      done = eng.record_side_event()
     self._stats['host_seconds'] += time.perf_counter() - t0
     self._stats['refills'] += 1
     self._stats['scenes'] += n

@@ -155,6 +155,30 @@ class OracleEngine(object):
   def check_render(self):
     pass
 
+  # the asynchronous refill's engine surface: no streams here, so a snapshot is a copy taken at
+  # once and every event has already happened
+  def snapshot_scene_serial(self):
+    serial = self._serial.copy()
+
+    class _Snapshot(object):
+      def ready(self):
+        return True
+
+      def wait(self):
+        return serial
+
+    return _Snapshot()
+
+  def side_stream_context(self):
+    import contextlib
+    return contextlib.nullcontext()
+
+  def record_side_event(self):
+    return None
+
+  def wait_event(self, event):
+    pass
+
   def download_state_serial(self):
     return self._serial.copy()
 

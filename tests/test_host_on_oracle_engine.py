@@ -135,3 +135,58 @@ def test_batched_environment_refill_never_serves_a_stale_scene():
     assert np.array_equal(ts.observation['image'].numpy(), bo.frames), t
   assert absolute.min() >= 2 * K           # every ring went round at least twice
   env.close()
+
+
+def test_batched_environment_async_refill_on_the_double():
+  """The asynchronous refill (worker thread, snapshots taken ahead of need, underflow guard) with
+  the oracle-backed engine double: at the fastest consumption the protocol allows no env ever
+  lands on a scene that was not uploaded for exactly that visit of its ring slot, and the outputs
+  equal an independent oracle's.  (On the device the same logic runs against streams and events:
+  tests/test_gpu_api.py.)"""
+  import numpy as np
+  from oracle import oracle
+  from spriteworld_b200 import constants, environment
+  from spriteworld_b200.configs.cobra import sorting
+  from tests import fixtures
+  cfg = sorting.get_config('train')
+  cfg['max_episode_length'] = 1           # FIRST, LAST, FIRST, ...: a scene every two steps
+  E, K, T = 48, 6, 80
+  env = environment.BatchedEnvironment(n_envs=E, pool_depth=K, rng=np.random.RandomState(5),
+                                       refill='async', **cfg)
+  eng = env.engine
+  uploads = np.ones((E, K), np.int64)      # the constructor filled every slot once
+  pushed = eng.upload_scenes
+
+  def upload(batch, env_ids, ring_slots):
+    np.add.at(uploads, (np.asarray(env_ids), np.asarray(ring_slots)), 1)
+    return pushed(batch, env_ids, ring_slots)
+
+  eng.upload_scenes = upload
+  nodes, _ = cfg['task'].compile()
+  ocfg = fixtures.env_cfg_from_meta(dict(action=cfg['action_space'].compile(), keep_in_frame=True,
+                                         max_episode_length=1, nodes=nodes))
+  bo = oracle.BatchOracle(ocfg, oracle.shape_table(constants.SHAPES), oracle.raster_cfg(64, 64, 5),
+                          eng._bo.pool.copy())
+  bo.pool = eng._bo.pool
+  absolute = np.zeros(E, np.int64)
+  last_cursor = np.zeros(E, np.int64)
+  rng = np.random.RandomState(11)
+  for t in range(T):
+    if t in (30, 31, 32):                  # explicit resets count against the ring too
+      ts = env.reset()
+      bo.reset_next[:] = 1
+      bo.step(np.zeros((E, 4), np.float32))
+    else:
+      a = rng.uniform(0, 1, (E, 4)).astype(np.float32)
+      ts = env.step(a)
+      bo.step(a)
+    cur = eng._bo.cursor.astype(np.int64)
+    absolute += (cur - last_cursor) % K
+    last_cursor = cur
+    assert np.array_equal(uploads[np.arange(E), absolute % K], absolute // K + 1), t
+    assert np.array_equal(ts.step_type.numpy(), bo.step_type), t
+    assert np.array_equal(ts.observation['image'].numpy(), bo.frames), t
+  stats = env.refill_stats()
+  assert stats['mode'] == 'async' and stats['refills'] >= 5
+  assert absolute.min() >= 2 * K
+  env.close()
