@@ -359,18 +359,16 @@ class BatchedEnvironment(object):
     self._last_snap = -(1 << 30)
     self._worker = None
     self._stats = dict(refills=0, scenes=0, host_seconds=0.0, blocked_seconds=0.0, blocked=0,
-                       sample_seconds=0.0, lock_wait_seconds=0.0, upload_seconds=0.0)
+                       collect_seconds=0.0, upload_seconds=0.0)
     if refill == 'async':
       import concurrent.futures
-      import threading
       self._worker = concurrent.futures.ThreadPoolExecutor(1, thread_name_prefix='swb-refill')
-      n_thr = max(1, min(int(refill_threads), E))
+      n_thr = max(1, min(max(int(refill_threads), int(refill_procs or 0)), E))
       # one RandomState per block of envs, so that the blocks' draws do not depend on timing
       # (never `rng` itself: the step thread draws the action noise from it)
       self._block_rngs = [np.random.RandomState(self._rng.randint(0, 2 ** 31 - 1))
                           for _ in range(n_thr)]
       self._block_edges = np.linspace(0, E, len(self._block_rngs) + 1).astype(np.int64)
-      self._upload_lock = threading.Lock()
       self._pool = None
       if refill_procs:
         from spriteworld_b200 import _sampler_pool
@@ -458,7 +456,6 @@ class BatchedEnvironment(object):
     K, n = self._K, 0
     edges = self._block_edges
     plans = [self._plan_block(serial, int(edges[i]), int(edges[i + 1])) for i in range(len(edges) - 1)]
-    self._stats['plan_seconds'] = self._stats.get('plan_seconds', 0.0) + time.perf_counter() - t0
     with eng.side_stream_context():
       if self._pool is not None:
         # every worker draws its block at the same time; collect and upload in block order
@@ -471,7 +468,7 @@ class BatchedEnvironment(object):
                   tc = time.perf_counter()
                   batch = self._pool.collect(j % len(self._pool))
                   t1 = time.perf_counter()
-                  self._stats['sample_seconds'] += t1 - tc   # waiting for / receiving the worker's block
+                  self._stats['collect_seconds'] += t1 - tc   # waiting for the worker's block
                   self._upload(None, plans[j][0], plans[j][1] % K, batch=batch)
                   self._stats['upload_seconds'] += time.perf_counter() - t1
       else:

@@ -16,6 +16,12 @@ def hsv_to_rgb(c):
   return tuple((255 * np.array(colorsys.hsv_to_rgb(*c))).astype(np.uint8))
 
 
+# which of (v, q, p, t) each channel takes in colorsys.hsv_to_rgb's cases i = 0..5
+_R_CASE = np.array([0, 1, 2, 2, 3, 0])
+_G_CASE = np.array([3, 0, 0, 1, 2, 2])
+_B_CASE = np.array([2, 2, 3, 0, 0, 1])
+
+
 def _hsv_arrays(h, s, v):
   """colorsys.hsv_to_rgb on arrays of one float dtype (elementwise IEEE ops, no fusion)."""
   dt = h.dtype.type
@@ -27,9 +33,15 @@ def _hsv_arrays(h, s, v):
   q = v * (one - s * f)
   t = v * (one - s * (one - f))
   i = i % 6
-  r = np.choose(i, [v, q, p, p, t, v])
-  g = np.choose(i, [t, v, v, q, p, p])
-  b = np.choose(i, [p, p, t, v, v, q])
+  # colorsys' six cases as one gather per channel from (v, q, p, t) laid end to end
+  # (np.choose over six arrays is four times slower)
+  flat = i.reshape(-1)
+  n = flat.shape[0]
+  vals = np.concatenate([v.reshape(-1), q.reshape(-1), p.reshape(-1), t.reshape(-1)])
+  base = np.arange(n)
+  r = vals[_R_CASE[flat] * n + base].reshape(i.shape)
+  g = vals[_G_CASE[flat] * n + base].reshape(i.shape)
+  b = vals[_B_CASE[flat] * n + base].reshape(i.shape)
   grey = s == 0
   if grey.any():
     r, g, b = np.where(grey, v, r), np.where(grey, v, g), np.where(grey, v, b)

@@ -56,6 +56,10 @@ def _ragged_concat(a, b):
   n = a.n
   tables = a.tables + b.tables
   count = a.count + b.count
+  if n and a.valid().all() and b.valid().all():   # no padding on either side: plain concatenation
+    return SceneLayout(tables, count,
+                       np.concatenate([a.ref_table, b.ref_table + len(a.tables)], axis=1),
+                       np.concatenate([a.ref_row, b.ref_row], axis=1))
   width = int(count.max()) if n else 0
   ref_table = np.zeros((n, width), np.int64)
   ref_row = np.zeros((n, width), np.int64)
