@@ -15,7 +15,7 @@
 //                 the row's list of VISIBLE segments (x range + sprite), i.e. the painter's
 //                 algorithm resolved once per canvas row.
 //   C  per sprite region (the outputs whose 2-D tap window can see the sprite), in tiles of
-//      up to three blocks of eight output rows x 21 columns:
+//      up to three blocks of eight output rows x 20 columns:
 //        H  horizontal LANCZOS pass of the canvas rows the tile needs.  A canvas row is
 //           piecewise constant, so an output is bg*K + sum_segments (colour-bg) * (P[b]-P[a])
 //           with P the prefix sums of the 22-bit tap vector and [a, b) the segment clamped
@@ -269,7 +269,6 @@ render_kernel(DevState st, RasterDev rd, const RenderLayout L, const RenderTarge
   int32_t *s_prefix = reinterpret_cast<int32_t *>(smem + L.off_prefix);
   uint32_t *s_xwin = reinterpret_cast<uint32_t *>(smem + L.off_xwin);
   uint32_t *s_ywin = reinterpret_cast<uint32_t *>(smem + L.off_ywin);
-  uint32_t *s_ht = reinterpret_cast<uint32_t *>(smem + L.off_scratch);
   uint8_t *s_frame = smem + L.off_frame;
   // phase-B view of the scratch area: per-row crossing lists
   const int CAP = L.cap;
