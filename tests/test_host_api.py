@@ -232,3 +232,30 @@ def test_sampler_pool_draws_what_the_in_process_sampler_draws():
         assert got[k].dtype == want[k].dtype and np.array_equal(got[k], want[k]), (k, n)
   finally:
     pool.close()
+
+
+@pytest.mark.parametrize('name', ['cobra.exploration', 'cobra.sorting', 'cobra.clustering',
+                                  'examples.goal_finding_clustering', 'examples.goal_finding_embodied'])
+def test_batched_packing_equals_packing_the_sprites_one_scene_at_a_time(name):
+  """scene.arrays_from_layout on a batch layout (several typed tables, merged when their columns
+  agree, ragged sprite counts, object columns) against the plain route: build the Sprite objects
+  of every scene from the same sampled factors and pack each scene on its own."""
+  import importlib
+  from spriteworld_b200 import scene, sprite, sprite_generators
+  cfg = importlib.import_module('spriteworld_b200.configs.' + name).get_config('train')
+  _, filters = cfg['task'].compile()
+  color_to_rgb = cfg['renderers']['image'].color_to_rgb
+  np.random.seed(4)
+  layout = sprite_generators.batch_of(cfg['init_sprites'], 96, np.random.RandomState(9))
+  n_slots = max(1, int(layout.count.max()))
+  got = scene.arrays_from_layout(layout, n_slots, filters, color_to_rgb)
+  for i in range(layout.n):
+    sprites = []
+    for j in range(int(layout.count[i])):
+      cols = layout.tables[layout.ref_table[i, j]].columns
+      row = layout.ref_row[i, j]
+      sprites.append(sprite.Sprite(**{k: v[row] for k, v in cols.items() if not k.startswith('_')}))
+    one = scene.arrays_from_layout(sprite_generators.layout_from_sprite_lists([sprites]), n_slots,
+                                   filters, color_to_rgb)
+    for k in one:
+      assert np.array_equal(got[k][i], one[k][0]), (name, i, k)
