@@ -1,4 +1,6 @@
-"""Builds spriteworld_b200/csrc/libspriteworld_b200.so with nvcc for sm_100a (in-tree).
+"""Builds spriteworld_b200/csrc/libspriteworld_b200.so with nvcc for sm_100a (in-tree), and the
+small host-side helper csrc/libswb_host.so (C, gcc: scene packing for the batched environment's
+refill; optional -- without it the NumPy path runs).
 
     python -m spriteworld_b200.build [--force]
 """
@@ -35,7 +37,29 @@ def is_stale():
   return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
+HOST_LIB = os.path.join(CSRC, 'libswb_host.so')
+HOST_SRC = os.path.join(CSRC, 'swb_host_pack.c')
+# parity with NumPy's elementwise float arithmetic: no contraction
+HOST_FLAGS = ['-O3', '-ffp-contract=off', '-fPIC', '-shared', '-Wall', '-Wextra']
+
+
+def build_host(force=False):
+  """libswb_host.so (gcc).  Returns its path, or None if there is no C compiler."""
+  if not force and os.path.exists(HOST_LIB) and os.path.getmtime(HOST_LIB) >= os.path.getmtime(HOST_SRC):
+    return HOST_LIB
+  cc = shutil.which('gcc') or shutil.which('cc')
+  if not cc:
+    return None
+  proc = subprocess.run([cc] + HOST_FLAGS + ['-o', HOST_LIB, HOST_SRC], stdout=subprocess.PIPE,
+                        stderr=subprocess.STDOUT, text=True)
+  if proc.returncode:
+    sys.stderr.write(proc.stdout)
+    raise RuntimeError('building libswb_host.so failed (%d)' % proc.returncode)
+  return HOST_LIB
+
+
 def build(force=False, verbose=False):
+  build_host(force)
   if not force and not is_stale():
     return LIB
   cmd = [_nvcc()] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', LIB] + SOURCES

@@ -15,6 +15,8 @@ import math
 
 import numpy as np
 
+from spriteworld_b200 import _host_pack
+
 F64_FIELDS = ('x', 'y', 'm00', 'm01', 'm10', 'm11', 'vx', 'vy')
 
 
@@ -206,12 +208,11 @@ def arrays_from_layout(layout, n_slots, filters=(), color_to_rgb=None):
     raise ValueError('a scene has %d sprites but the engine has %d slots'
                      % (int(layout.count.max()), n_slots))
   tables, offsets = _merged_tables(layout.tables)
-  per_table = [None if t.rows == 0 else _table_arrays(t, filters, color_to_rgb) for t in tables]
   n = layout.n
   valid = layout.valid()
   full = bool(valid.all()) and layout.width == n_slots    # every slot of every scene gets written
   b = empty_batch(n, n_slots, zero=not full)
-  if valid.all() and layout.width == n_slots:      # every slot of every scene is taken
+  if full:
     flat_dst = None
     tab, row = layout.ref_table.reshape(-1), layout.ref_row.reshape(-1)
   else:
@@ -221,6 +222,10 @@ def arrays_from_layout(layout, n_slots, filters=(), color_to_rgb=None):
   if offsets is not None:
     row = row + offsets[tab]                        # the tables were concatenated into one
     tab = None
+  if (tab is None or len(tables) == 1) and tables and tables[0].rows and _host_pack.pack(
+      tables[0], filters, color_to_rgb, row, flat_dst, b):
+    return b                                        # one native pass over the sprites
+  per_table = [None if t.rows == 0 else _table_arrays(t, filters, color_to_rgb) for t in tables]
   fields = ('x', 'y', 'm00', 'm01', 'm10', 'm11', 'vx', 'vy', 'member', 'shape', 'pos_f32', 'rgb', 'factors')
   for t, data in enumerate(per_table):
     if data is None:

@@ -259,3 +259,54 @@ def test_batched_packing_equals_packing_the_sprites_one_scene_at_a_time(name):
                                    filters, color_to_rgb)
     for k in one:
       assert np.array_equal(got[k][i], one[k][0]), (name, i, k)
+
+
+def _pack_both_ways(layout, n_slots, filters, color_to_rgb, monkeypatch):
+  from spriteworld_b200 import _host_pack, scene
+  native = scene.arrays_from_layout(layout, n_slots, filters, color_to_rgb)
+  with monkeypatch.context() as m:
+    m.setattr(_host_pack, 'pack', lambda *a, **k: False)
+    plain = scene.arrays_from_layout(layout, n_slots, filters, color_to_rgb)
+  return native, plain
+
+
+def test_native_packing_equals_the_numpy_path(monkeypatch):
+  """csrc/swb_host_pack.c (one pass per sprite: gathers, HSV colour map in the factors' float
+  type, shape ids by object pointer) against the NumPy path it shortcuts, value for value: the
+  shipped configs, float64 and integer-RGB colours, grey and hue-1.0 corner cases, ragged counts."""
+  import importlib
+  from spriteworld_b200 import _host_pack, factor_distributions as distribs
+  from spriteworld_b200 import sprite_generators as gen
+  from spriteworld_b200.renderers import color_maps
+  if _host_pack.load() is None:
+    pytest.skip('libswb_host.so has not been built')
+  used = []
+  real = _host_pack.pack
+  monkeypatch.setattr(_host_pack, 'pack', lambda *a, **k: used.append(real(*a, **k)) or used[-1])
+  cases = []
+  for name in ('cobra.sorting', 'cobra.clustering', 'cobra.exploration', 'cobra.goal_finding_more_targets',
+               'examples.goal_finding_clustering'):
+    cfg = importlib.import_module('spriteworld_b200.configs.' + name).get_config('train')
+    cases.append((name, cfg['init_sprites'], cfg['task'].compile()[1], cfg['renderers']['image'].color_to_rgb))
+  corner = distribs.Product([
+      distribs.Continuous('x', 0., 1.), distribs.Continuous('y', 0., 1., dtype='float64'),
+      distribs.Discrete('shape', ['star_5', 'circle', 'spoke_4']), distribs.Continuous('angle', 0., 360.),
+      distribs.Continuous('scale', 0.05, 0.3, dtype='float64'),
+      distribs.Discrete('c0', [0.0, 1.0, 0.999999, 0.16666667, 0.5]), distribs.Discrete('c1', [0.0, 1.0, 0.3]),
+      distribs.Continuous('c2', 0., 1., dtype='float64'), distribs.Continuous('x_vel', -.1, .1)])
+  cases.append(('float64 hsv corners', gen.generate_sprites(corner, lambda: np.random.randint(0, 5)),
+                [distribs.Continuous('c2', 0.2, 0.7)], color_maps.hsv_to_rgb))
+  rgb = distribs.Product([distribs.Continuous('x', 0., 1.), distribs.Continuous('y', 0., 1.),
+                          distribs.Discrete('c0', [0, 128, 255]), distribs.Discrete('c1', [3, 200]),
+                          distribs.Discrete('c2', [77])])
+  cases.append(('integer rgb', gen.generate_sprites(rgb, 3), [], None))
+  for name, generator, filters, color_to_rgb in cases:
+    np.random.seed(2)
+    layout = gen.batch_of(generator, 300, np.random.RandomState(1))
+    n_slots = max(1, int(layout.count.max()))
+    before = len(used)
+    native, plain = _pack_both_ways(layout, n_slots, filters, color_to_rgb, monkeypatch)
+    if name != 'examples.goal_finding_clustering':   # (its tables have different columns: NumPy path)
+      assert used[before:] == [True], (name, used[before:])   # the native pass did run
+    for k in plain:
+      assert native[k].dtype == plain[k].dtype and np.array_equal(native[k], plain[k]), (name, k)
